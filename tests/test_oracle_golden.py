@@ -1,0 +1,103 @@
+"""CPU: pins the oracle restatements (oracle/*.py) against fixtures generated
+from the reference's own modules (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ivosw import synth
+from oracle import assess_ref, brain_ref, manet_tail_ref, round_ref
+
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def test_boxes_known_answers(golden_dir):
+    g = _load(golden_dir, "boxes")
+    masks = np.unpackbits(g["masks"], axis=-1)[..., :854].astype(np.float32)
+    got = assess_ref.all2yxhw(masks, scale=1.5)
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got, g["boxes"])          # bit-exact: integer/float64 arithmetic
+    # SURVEY §8(a) a3 verified cases
+    np.testing.assert_array_equal(got[0], [199.5, 349.5, 300, 450])
+    np.testing.assert_array_equal(got[1], [204.5, 402, 192, 193.5])
+    np.testing.assert_array_equal(got[2], [240, 427, 491, 865])
+    np.testing.assert_array_equal(got[3], [240, 427, 491, 865])
+    np.testing.assert_array_equal(assess_ref.all2yxhw(g["small"], 1.5), g["boxes_small"])
+
+
+def test_brain_matches_reference(golden_dir):
+    g = _load(golden_dir, "brain")
+    for seed in (0, 1):
+        sd = {k: v.numpy() for k, v in synth.brain_state_dict(seed).items()}
+        for (N, T) in ((1, 1), (1, 8), (1, 64), (1, 128), (4, 25)):
+            x = g["s%d_N%d_T%d_x" % (seed, N, T)]
+            q64 = brain_ref.brain_forward(sd, x, np.float64)
+            np.testing.assert_allclose(q64, g["s%d_N%d_T%d_f64_q" % (seed, N, T)], rtol=0, atol=1e-12)
+            q32 = brain_ref.brain_forward(sd, x, np.float32)
+            ref32 = g["s%d_N%d_T%d_f32_q" % (seed, N, T)]
+            np.testing.assert_allclose(q32, ref32, rtol=0, atol=2e-6)
+            assert (q32.argmax(1) == ref32.argmax(1)).all()
+
+
+def test_grid_sample_restatement_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand((3, 4, 37, 53), generator=g)
+    roi = torch.tensor([[18., 26., 50., 70.], [5., 5., 20., 20.], [30., 50., 30., 30.]])
+    gx, gy = assess_ref.roi_grid(roi, (37, 53), 64)
+    mine = assess_ref.grid_sample_bilinear(img, gx, gy)
+    theta = torch.zeros(3, 2, 3)
+    t00, t02, t11, t12 = assess_ref.roi_theta(roi, (37, 53))
+    theta[:, 0, 0], theta[:, 0, 2], theta[:, 1, 1], theta[:, 1, 2] = t00, t02, t11, t12
+    grid = torch.nn.functional.affine_grid(theta, (3, 1, 64, 64), align_corners=True)
+    np.testing.assert_array_equal(torch.stack([gx, gy], -1).numpy(), grid.numpy())   # bit-exact grid
+    ref = torch.nn.functional.grid_sample(img, grid, align_corners=True)
+    np.testing.assert_allclose(mine.numpy(), ref.numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["round_c1", "round_atnet_small", "round_single", "round_t16"])
+def test_round_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    clip_id, T, H, W, O, seed = [int(v) for v in g["meta"]]
+    all_F, all_P, annotated = synth.make_clip(clip_id, T, H, W, O, str(g["style"]))
+    assert annotated == [int(v) for v in g["annotated"]]
+    assess_sd, brain_sd = synth.assess_state_dict(seed), synth.brain_state_dict(seed)
+    # stage probes
+    for o in range(O):
+        pr = {}
+        s = assess_ref.assess_forward(assess_sd, torch.from_numpy(all_F), torch.from_numpy(all_P[:, o + 1]), probes=pr)
+        np.testing.assert_array_equal(pr["boxes"].numpy(), g["f32_boxes"][o])
+        np.testing.assert_allclose(pr["tf_roi"][:, ::1, ::8, ::8].numpy(), g["roi_f"][o], atol=5e-6)
+        np.testing.assert_allclose(pr["tp_roi"][:, ::8, ::8].numpy(), g["roi_p"][o], atol=5e-6)
+        for k, step in (("pool", 8), ("r2", 8), ("r3", 4), ("r4", 2), ("r5", 1)):
+            t = pr[k]
+            probe = t[:, ::max(1, t.shape[1] // 8), ::step, ::step].numpy()
+            np.testing.assert_allclose(probe, g[k][o], atol=2e-5, rtol=1e-5)
+        np.testing.assert_allclose(s.numpy(), g["f32_scores"][:, o], atol=2e-5)
+    mq = np.zeros(T)
+    r = round_ref.recommend_frame_wild_ours(assess_sd, brain_sd, all_F, all_P, annotated, mask_quality=mq)
+    np.testing.assert_allclose(mq, g["f32_mask_quality"], atol=2e-5)
+    np.testing.assert_allclose(r["q"], g["f32_q"], atol=2e-6)
+    assert r["next_frame"] == int(g["f32_next_frame"]) == int(g["f64_next_frame"])
+
+
+def test_round_fp64_arbiter(golden_dir):
+    g = _load(golden_dir, "round_atnet_small")
+    clip_id, T, H, W, O, seed = [int(v) for v in g["meta"]]
+    all_F, all_P, annotated = synth.make_clip(clip_id, T, H, W, O, str(g["style"]))
+    r = round_ref.recommend_frame_wild_ours(synth.assess_state_dict(seed), synth.brain_state_dict(seed),
+                                            all_F, all_P, annotated, dtype=torch.float64)
+    np.testing.assert_allclose(r["mask_quality"], g["f64_mask_quality"], atol=1e-9)
+    np.testing.assert_allclose(r["q"], g["f64_q"], atol=1e-10)
+
+
+def test_manet_tail(golden_dir):
+    g = _load(golden_dir, "manet_tail")
+    H, W = [int(v) for v in g["hw"]]
+    masks, all_P = manet_tail_ref.manet_tail(g["logits"], H, W)
+    np.testing.assert_array_equal(masks.numpy().astype(np.uint8), g["masks"])
+    np.testing.assert_allclose(all_P.numpy(), g["all_P"], atol=1e-7)
