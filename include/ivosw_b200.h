@@ -1,0 +1,159 @@
+/*
+ * ivosw_b200 — C ABI of the B200-native frame-scoring path of IVOS-W.
+ *
+ * The reference (svip-lab/IVOS-W) is pure Python and has no FFI of its own; the
+ * boundary it exposes for this path is three Python call signatures
+ * (SURVEY.md §8(b)):
+ *   B1  models/agent.py:168        Agent.action(state[T,2]) -> int
+ *       models/agent.py:33         Brain.forward(N x T x 2) -> N x T
+ *   B2  models/assessment.py:164   AssessNet.forward(tf B x 3 x H x W, tp B x H x W) -> B x 1
+ *   a1  utils/utils_agent.py:77    recommend_frame(...)  (setting='wild', method='ours', lines 111-122)
+ *   a10 utils/utils_manet.py:76-81,160-161  upsample / argmax / softmax tail of get_results
+ * Each entry point below names the reference interface it sits under.  The
+ * Python drop-in modules (ivos-w_b200/dropin/{models,utils}/) keep those
+ * signatures and call this library through ctypes; INTEGRATION.md shows the
+ * binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - *_dev pointers are caller-owned device memory on the context's device,
+ *     *_host pointers are caller-owned host memory (pinned or pageable);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the
+ *     legacy default stream) and is NOT synchronised unless stated;
+ *   - the only memory the library owns is the context's weights + workspace,
+ *     released by ivosw_destroy();
+ *   - every function returns IVOSW_OK (0) or an error code; the message is
+ *     available (thread-local) from ivosw_last_error().  An allocation failure
+ *     returns IVOSW_ERR_OOM and a message containing "out of memory", which
+ *     the Python shim re-raises as RuntimeError so that the reference's
+ *     OOM-retry loop (eval_agent_manet.py:382-396) keeps working.
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef IVOSW_B200_H
+#define IVOSW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVOSW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define IVOSW_API __attribute__((visibility("default")))
+#else
+#define IVOSW_API
+#endif
+
+enum ivosw_status {
+    IVOSW_OK = 0,
+    IVOSW_ERR_INVALID = 1, /* bad argument / shape */
+    IVOSW_ERR_CUDA = 2,    /* CUDA runtime / driver error */
+    IVOSW_ERR_OOM = 3,     /* cudaErrorMemoryAllocation: message contains "out of memory" */
+    IVOSW_ERR_STATE = 4    /* weights not loaded, wrong device, ... */
+};
+
+/* How the ResNet-50 convolutions of AssessNet are evaluated. */
+enum ivosw_conv_mode {
+    IVOSW_CONV_SIMT_FP32 = 0, /* fp32 CUDA-core implicit GEMM: validation path                     */
+    IVOSW_CONV_TC_FP16X3 = 1, /* tcgen05 kind::f16, split-fp16 operands, 3 MMA terms: fp32-grade   */
+    IVOSW_CONV_TC_FP16X1 = 2  /* tcgen05 kind::f16, single fp16 term: fast, ~1e-3 relative         */
+};
+
+typedef struct ivosw_ctx ivosw_ctx;
+
+IVOSW_API int ivosw_abi_version(void);
+IVOSW_API const char* ivosw_last_error(void);
+
+/* Creates a context on CUDA device `device`. */
+IVOSW_API int ivosw_create(int device, int conv_mode, ivosw_ctx** out);
+IVOSW_API void ivosw_destroy(ivosw_ctx* ctx);
+IVOSW_API int ivosw_set_conv_mode(ivosw_ctx* ctx, int conv_mode);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+IVOSW_API long long ivosw_launch_count(const ivosw_ctx* ctx);
+
+/* ---- Q-network (models/agent.py::Brain) --------------------------------------------------
+ * params_host: the 180 993 floats of Brain.state_dict() concatenated in this order
+ * (row-major, torch layout): encoder_fc1.weight[128x2], encoder_fc1.bias[128],
+ * encoder_fc2.weight[128x128], encoder_fc2.bias[128], lstm_cell.weight_ih[512x128],
+ * lstm_cell.weight_hh[512x128], decoder_fc1.weight[128x256], decoder_fc1.bias[128],
+ * decoder_fc2.weight[1x128], decoder_fc2.bias[1]. */
+#define IVOSW_BRAIN_NUM_PARAMS 180993
+IVOSW_API int ivosw_brain_load(ivosw_ctx* ctx, const float* params_host, size_t n_floats);
+
+/* Brain.forward (models/agent.py:33-64) + the first-max argmax of Agent.action (:187-188).
+ * state_dev: N x T x 2 fp32; q_dev: N x T fp32; argmax_dev: N int32 (may be NULL). */
+IVOSW_API int ivosw_brain_forward(ivosw_ctx* ctx, const float* state_dev, int N, int T,
+                        float* q_dev, int* argmax_dev, void* stream);
+
+/* ---- quality CNN (models/assessment.py::AssessNet) ---------------------------------------
+ * blob_host: fp32, in this order
+ *   mean[3], std[3]                                        (Encoder.mean / Encoder.std)
+ *   stem weight [64][7][7][4]  (cout, kh, kw, cin; cin 0..2 = Encoder.conv1, cin 3 = Encoder.conv1_p)
+ *   stem BN: weight[64], bias[64], running_mean[64], running_var[64]      (Encoder.bn1)
+ *   for each of the 52 convs of res2..res5 in execution order (per block: conv1, conv2,
+ *   [downsample.0 if first block of the stage], conv3):
+ *       weight [cout][kh][kw][cin], BN weight[cout], bias[cout], running_mean[cout], running_var[cout]
+ *   fc1.weight[2048], fc1.bias[1]
+ * ivosw_assess_blob_floats() returns the expected length. */
+IVOSW_API size_t ivosw_assess_blob_floats(void);
+IVOSW_API int ivosw_assess_load(ivosw_ctx* ctx, const float* blob_host, size_t n_floats);
+
+/* AssessNet.forward (models/assessment.py:164-182).
+ * frames_dev: B x 3 x H x W fp32 NCHW, frame b at frames_dev + b*frame_stride (floats);
+ * prob_dev:   B planes of H x W fp32, plane b at prob_dev + b*prob_stride (floats) — so
+ *             all_P[:, i+1] of a T x (O+1) x H x W tensor is passed without a copy;
+ * score_dev:  B fp32.  boxes_dev (nullable): B x 4 fp32 [yc, xc, h, w] of all2yxhw (:110-161). */
+IVOSW_API int ivosw_assess_forward(ivosw_ctx* ctx, const float* frames_dev, long long frame_stride,
+                         const float* prob_dev, long long prob_stride, int B, int H, int W,
+                         float* score_dev, float* boxes_dev, void* stream);
+
+/* Parity probes (tests only).  After ivosw_enable_probes(ctx, 1) every ivosw_assess_forward
+ * keeps the intermediates of its LAST chunk; ivosw_assess_probe converts one of them to NCHW
+ * fp32 in out_dev.  which: 0 ROI crop (4 x 256 x 256: normalised RGB + prob), 1 after maxpool
+ * (64 x 64 x 64), 2..5 r2..r5.  dims4_out receives {n, c, h, w}. */
+IVOSW_API int ivosw_enable_probes(ivosw_ctx* ctx, int enable);
+IVOSW_API int ivosw_assess_probe(ivosw_ctx* ctx, int which, float* out_dev, size_t capacity_floats,
+                       int* dims4_out, void* stream);
+
+/* ---- one scoring round (utils/utils_agent.py::recommend_frame, wild/ours, :111-122) -------
+ * frames_dev: T x 3 x H x W; probs_dev: T x (O+1) x H x W (channel 0 = background, unused);
+ * annotated_counts_host: T doubles (histogram of annotated frames, :112-113).
+ * Scores frames [t_begin, t_end) for every object, averages over objects in fp64 (:120),
+ * and — when the range covers the whole clip — runs Brain and the argmax on device.
+ * Outputs (host, written after an internal stream synchronise):
+ *   mask_quality_host[t_end - t_begin] doubles, scores_host (nullable) (t_end-t_begin) x O fp32,
+ *   q_host (nullable) T fp32, next_frame (nullable) int.
+ * q_host / next_frame are only produced when t_begin == 0 && t_end == T. */
+IVOSW_API int ivosw_round_device(ivosw_ctx* ctx, const float* frames_dev, const float* probs_dev,
+                       int T, int O, int H, int W, int t_begin, int t_end,
+                       const double* annotated_counts_host, double* mask_quality_host,
+                       float* scores_host, float* q_host, int* next_frame, void* stream);
+
+/* Same round from HOST buffers (the end-to-end path bench.py reports as `e2e`): the
+ * host->device copies of frames and probabilities are issued inside the call, in
+ * frame chunks that overlap with the scoring of the previous chunk. */
+IVOSW_API int ivosw_round_host(ivosw_ctx* ctx, const float* frames_host, const float* probs_host,
+                     int T, int O, int H, int W,
+                     const double* annotated_counts_host, double* mask_quality_host,
+                     float* scores_host, float* q_host, int* next_frame, void* stream);
+
+/* Brain + argmax on an already gathered quality vector (multi-GPU: after the all-gather).
+ * mask_quality_host: T doubles; annotated_counts_host: T doubles. Synchronises. */
+IVOSW_API int ivosw_agent_action(ivosw_ctx* ctx, const double* mask_quality_host,
+                       const double* annotated_counts_host, int T,
+                       float* q_host, int* next_frame, void* stream);
+
+/* ---- MANet round tail (utils/utils_manet.py:76-81,109-114,146-150,160-161) ---------------
+ * logits_dev: T x C x h x w fp32 (C = O+1).  Bilinear upsample (align_corners=True) to
+ * H x W, per-pixel first-max argmax -> masks_dev (T x H x W fp32, nullable), channel
+ * softmax -> all_p_dev (T x C x H x W fp32, nullable). */
+IVOSW_API int ivosw_manet_tail(ivosw_ctx* ctx, const float* logits_dev, int T, int C, int h, int w,
+                     int H, int W, float* masks_dev, float* all_p_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVOSW_B200_H */

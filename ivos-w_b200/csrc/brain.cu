@@ -1,0 +1,227 @@
+// Q-network: models/agent.py::Brain.forward (lines 33-64) + the first-max argmax of Agent.action
+// (lines 187-188), as three launches instead of the reference's ~20 library calls per frame:
+//
+//   brain_inproj_kernel     all frames in parallel:  e_t = fc2(relu(fc1(x_t)));  gi_t = W_ih e_t.
+//                           The same LSTMCell serves both directions (agent.py:48-49), so gi_t is
+//                           computed once and shared by the forward and backward chains.
+//   brain_recurrent_kernel  one CTA per (direction, batch row): the T-step dependency chain
+//                           gates = gi_t + W_hh h_{t-1} with W_hh resident on chip (half in
+//                           registers, half in shared memory), zero initial state, gate order i,f,g,o,
+//                           no bias (LSTMCell(..., bias=False), agent.py:24-25).
+//   brain_decode_kernel     Q_t = fc_d2(relu(fc_d1(relu([h_fw_t ; h_bw_t]))))  (agent.py:55-60) and
+//                           argmax over t, first maximum wins (numpy semantics).
+//
+// Latency-bound (2T dependent steps); weights are 724 KB and stay in L2 / on chip.
+#include "ivosw_internal.h"
+
+namespace ivosw {
+
+// offsets (floats) into the canonical parameter blob, see include/ivosw_b200.h
+constexpr int P_FC1W = 0;
+constexpr int P_FC1B = P_FC1W + 128 * 2;
+constexpr int P_FC2W = P_FC1B + 128;
+constexpr int P_FC2B = P_FC2W + 128 * 128;
+constexpr int P_WIH = P_FC2B + 128;
+constexpr int P_WHH = P_WIH + 512 * 128;
+constexpr int P_D1W = P_WHH + 512 * 128;
+constexpr int P_D1B = P_D1W + 128 * 256;
+constexpr int P_D2W = P_D1B + 128;
+constexpr int P_D2B = P_D2W + 128;
+static_assert(P_D2B + 1 == IVOSW_BRAIN_NUM_PARAMS, "Brain parameter count");
+
+__device__ inline float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) brain_inproj_kernel(const float* __restrict__ P,
+                                                           const float* __restrict__ state,  // [N][T][2]
+                                                           int T, float* __restrict__ GI) {    // [N][T][512]
+    __shared__ float sa[128], se[128];
+    const int t = blockIdx.x, n = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float x0 = state[((long long)n * T + t) * 2 + 0], x1 = state[((long long)n * T + t) * 2 + 1];
+    if (threadIdx.x < 128) {
+        int j = threadIdx.x;
+        float v = fmaf(P[P_FC1W + 2 * j + 1], x1, fmaf(P[P_FC1W + 2 * j], x0, 0.f)) + P[P_FC1B + j];
+        sa[j] = fmaxf(v, 0.f);
+    }
+    __syncthreads();
+    const float a0 = sa[lane], a1 = sa[lane + 32], a2 = sa[lane + 64], a3 = sa[lane + 96];
+    for (int j = warp; j < 128; j += 16) {
+        const float* w = P + P_FC2W + j * 128;
+        float v = w[lane] * a0 + w[lane + 32] * a1 + w[lane + 64] * a2 + w[lane + 96] * a3;
+        v = warp_sum(v);
+        if (lane == 0) se[j] = v + P[P_FC2B + j];   // no ReLU after fc2 (agent.py:46)
+    }
+    __syncthreads();
+    const float e0 = se[lane], e1 = se[lane + 32], e2 = se[lane + 64], e3 = se[lane + 96];
+    float* gi = GI + ((long long)n * T + t) * 512;
+    for (int j = warp; j < 512; j += 16) {
+        const float* w = P + P_WIH + j * 128;
+        float v = w[lane] * e0 + w[lane + 32] * e1 + w[lane + 64] * e2 + w[lane + 96] * e3;
+        v = warp_sum(v);
+        if (lane == 0) gi[j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// whh_pack: [32][512] float4, whh_pack[kq][j] = W_hh[j][4kq .. 4kq+3]
+__global__ void brain_pack_whh_kernel(const float* __restrict__ whh, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 32 * 512
+    if (i >= 32 * 512) return;
+    int kq = i / 512, j = i - kq * 512;
+    const float* r = whh + j * 128 + kq * 4;
+    out[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+__device__ inline float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(512, 1) brain_recurrent_kernel(const float4* __restrict__ whh_pack,
+                                                                 const float* __restrict__ GI,  // [N][T][512]
+                                                                 int T, float* __restrict__ Hout) {  // [N][2][T][128]
+    extern __shared__ __align__(16) float4 sW[];           // [16][512] float4 : k = 64..127
+    float* sg = reinterpret_cast<float*>(sW + 16 * 512);   // 512 gate pre-activations
+    float* sh = sg + 512;                                  // 128 hidden state
+    const int dir = blockIdx.x, n = blockIdx.y, j = threadIdx.x;
+    float4 wr[16];                                         // k = 0..63 in registers
+#pragma unroll
+    for (int kq = 0; kq < 16; ++kq) wr[kq] = whh_pack[kq * 512 + j];
+    for (int kq = 0; kq < 16; ++kq) sW[kq * 512 + j] = whh_pack[(16 + kq) * 512 + j];
+    if (j < 128) sh[j] = 0.f;
+    float c = 0.f;
+    const float* gi = GI + (long long)n * T * 512;
+    float* ho = Hout + ((long long)n * 2 + dir) * T * 128;
+    int t = dir == 0 ? 0 : T - 1;
+    float gi_cur = gi[(long long)t * 512 + j];
+    __syncthreads();
+    const float4* sh4 = reinterpret_cast<const float4*>(sh);
+    for (int s = 0; s < T; ++s) {
+        const int tn = dir == 0 ? t + 1 : t - 1;
+        float gi_next = 0.f;
+        if (s + 1 < T) gi_next = gi[(long long)tn * 512 + j];   // prefetch across the step
+        float a0 = gi_cur, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int kq = 0; kq < 16; ++kq) {
+            const float4 h = sh4[kq];
+            a0 = fmaf(wr[kq].x, h.x, a0); a1 = fmaf(wr[kq].y, h.y, a1);
+            a2 = fmaf(wr[kq].z, h.z, a2); a3 = fmaf(wr[kq].w, h.w, a3);
+        }
+#pragma unroll
+        for (int kq = 0; kq < 16; ++kq) {
+            const float4 h = sh4[16 + kq];
+            const float4 w = sW[kq * 512 + j];
+            a0 = fmaf(w.x, h.x, a0); a1 = fmaf(w.y, h.y, a1);
+            a2 = fmaf(w.z, h.z, a2); a3 = fmaf(w.w, h.w, a3);
+        }
+        sg[j] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (j < 128) {
+            const float ig = sigmoidf_(sg[j]), fg = sigmoidf_(sg[128 + j]);
+            const float gg = tanhf(sg[256 + j]), og = sigmoidf_(sg[384 + j]);
+            c = fmaf(fg, c, ig * gg);
+            const float h = og * tanhf(c);
+            sh[j] = h;
+            ho[(long long)t * 128 + j] = h;
+        }
+        __syncthreads();
+        t = tn;
+        gi_cur = gi_next;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) brain_decode_kernel(const float* __restrict__ P,
+                                                               const float* __restrict__ Hout,  // [N][2][T][128]
+                                                               int T, float* __restrict__ Q,     // [N][T]
+                                                               int* __restrict__ argmax) {
+    extern __shared__ __align__(16) float sm[];
+    float* sWt = sm;                    // [256][128]: decoder_fc1.weight transposed
+    float* ss = sWt + 256 * 128;        // [8][256] relu'd concatenated state per group
+    float* sred = ss + 8 * 256;         // [8][4]
+    const int n = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < 128 * 256; i += 1024) {
+        int jj = i >> 8, k = i & 255;   // coalesced read of W[jj][k]
+        sWt[k * 128 + jj] = P[P_D1W + i];
+    }
+    const int g = tid >> 7, j = tid & 127, wig = (tid >> 5) & 3, lane = tid & 31;
+    const float b1 = P[P_D1B + j], w2 = P[P_D2W + j], b2 = P[P_D2B];
+    const float* hf = Hout + ((long long)n * 2 + 0) * T * 128;
+    const float* hb = Hout + ((long long)n * 2 + 1) * T * 128;
+    float* s = ss + g * 256;
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += 8) {   // uniform trip count: all 1024 threads hit every barrier
+        const int t = t0 + g;
+        if (t < T) {
+            s[j] = fmaxf(hf[(long long)t * 128 + j], 0.f);
+            s[128 + j] = fmaxf(hb[(long long)t * 128 + j], 0.f);
+        }
+        __syncthreads();
+        float part = 0.f;
+        if (t < T) {
+            float a0 = b1, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 256; k += 4) {
+                a0 = fmaf(sWt[(k + 0) * 128 + j], s[k + 0], a0);
+                a1 = fmaf(sWt[(k + 1) * 128 + j], s[k + 1], a1);
+                a2 = fmaf(sWt[(k + 2) * 128 + j], s[k + 2], a2);
+                a3 = fmaf(sWt[(k + 3) * 128 + j], s[k + 3], a3);
+            }
+            part = w2 * fmaxf((a0 + a1) + (a2 + a3), 0.f);
+        }
+        part = warp_sum(part);
+        if (lane == 0) sred[g * 4 + wig] = part;
+        __syncthreads();
+        if (t < T && j == 0) Q[(long long)n * T + t] = ((sred[g * 4] + sred[g * 4 + 1]) + (sred[g * 4 + 2] + sred[g * 4 + 3])) + b2;
+    }
+    __syncthreads();
+    if (argmax && tid < 32) {   // first maximum wins (numpy argmax)
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int t = lane; t < T; t += 32) {
+            float v = Q[(long long)n * T + t];
+            if (v > best) { best = v; bi = t; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) argmax[n] = (bi == 0x7fffffff) ? 0 : bi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+int brain_pack(ivosw_ctx* c) {
+    if (!c->brain_whh_t) IVOSW_CUDA(cudaMalloc(&c->brain_whh_t, sizeof(float4) * 32 * 512));
+    brain_pack_whh_kernel<<<(32 * 512 + 255) / 256, 256>>>(c->brain_params + P_WHH, (float4*)c->brain_whh_t);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
+    const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
+    IVOSW_CUDA(cudaFuncSetAttribute(brain_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_smem));
+    IVOSW_CUDA(cudaFuncSetAttribute(brain_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+    IVOSW_CUDA(cudaDeviceSynchronize());
+    return IVOSW_OK;
+}
+
+int launch_brain(ivosw_ctx* c, const float* state, int N, int T, float* q, int* argmax, cudaStream_t s) {
+    int rc;
+    if ((rc = ensure(c->brain_gi, sizeof(float) * (size_t)N * T * 512))) return rc;
+    if ((rc = ensure(c->brain_h, sizeof(float) * (size_t)N * 2 * T * 128))) return rc;
+    brain_inproj_kernel<<<dim3(T, N), 512, 0, s>>>(c->brain_params, state, T, (float*)c->brain_gi.p);
+    IVOSW_CUDA(cudaGetLastError());
+    const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
+    brain_recurrent_kernel<<<dim3(2, N), 512, rec_smem, s>>>((const float4*)c->brain_whh_t, (const float*)c->brain_gi.p, T,
+                                                             (float*)c->brain_h.p);
+    IVOSW_CUDA(cudaGetLastError());
+    const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
+    brain_decode_kernel<<<N, 1024, dec_smem, s>>>(c->brain_params, (const float*)c->brain_h.p, T, q, argmax);
+    IVOSW_CUDA(cudaGetLastError());
+    c->launches += 3;
+    return IVOSW_OK;
+}
+
+}  // namespace ivosw

@@ -1,0 +1,483 @@
+// C-ABI entry points (include/ivosw_b200.h): context, weight loading, orchestration of the kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "ivosw_internal.h"
+
+namespace ivosw {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string& msg) { g_err = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    if (e == cudaErrorMemoryAllocation) {
+        snprintf(buf, sizeof buf, "CUDA out of memory (%s at %s:%d)", what, file, line);
+        g_err = buf;
+        cudaGetLastError();
+        return IVOSW_ERR_OOM;
+    }
+    snprintf(buf, sizeof buf, "CUDA error %d (%s): %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    g_err = buf;
+    cudaGetLastError();
+    return IVOSW_ERR_CUDA;
+}
+
+int ensure(DeviceBuffer& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return IVOSW_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    size_t want = (bytes + 255) & ~(size_t)255;
+    IVOSW_CUDA(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return IVOSW_OK;
+}
+
+void release(DeviceBuffer& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+}
+
+std::vector<ConvLayer> make_resnet50_layers() {
+    // mirrors ivosw/arch.py::resnet50_convs — torchvision Bottleneck, stride on the 3x3 conv
+    std::vector<ConvLayer> v;
+    const int planes_[4] = {64, 128, 256, 512}, blocks_[4] = {3, 4, 6, 3}, stride_[4] = {1, 2, 2, 2};
+    int inplanes = 64, hw = 64;
+    for (int st = 0; st < 4; ++st) {
+        for (int b = 0; b < blocks_[st]; ++b) {
+            const int s = b == 0 ? stride_[st] : 1, planes = planes_[st], out_hw = hw / s;
+            ConvLayer c1{}; c1.cin = inplanes; c1.cout = planes; c1.k = 1; c1.stride = 1; c1.pad = 0;
+            c1.in_hw = hw; c1.out_hw = hw; c1.relu = true; c1.residual = 0; c1.first_of_block = true;
+            v.push_back(c1);
+            ConvLayer c2{}; c2.cin = planes; c2.cout = planes; c2.k = 3; c2.stride = s; c2.pad = 1;
+            c2.in_hw = hw; c2.out_hw = out_hw; c2.relu = true;
+            v.push_back(c2);
+            if (b == 0) {
+                ConvLayer d{}; d.cin = inplanes; d.cout = planes * 4; d.k = 1; d.stride = s; d.pad = 0;
+                d.in_hw = hw; d.out_hw = out_hw; d.relu = false; d.is_downsample = true;
+                v.push_back(d);
+            }
+            ConvLayer c3{}; c3.cin = planes; c3.cout = planes * 4; c3.k = 1; c3.stride = 1; c3.pad = 0;
+            c3.in_hw = out_hw; c3.out_hw = out_hw; c3.relu = true; c3.residual = b == 0 ? 2 : 1;
+            v.push_back(c3);
+            inplanes = planes * 4;
+            hw = out_hw;
+        }
+    }
+    return v;
+}
+
+static size_t assess_blob_floats() {
+    size_t n = 6 + (size_t)64 * 49 * 4 + 4 * 64;
+    for (const ConvLayer& L : make_resnet50_layers()) n += (size_t)L.cout * L.k * L.k * L.cin + 4 * (size_t)L.cout;
+    return n + 2048 + 1;
+}
+
+static int upload(float** dst, const float* src, size_t n) {
+    if (!*dst) IVOSW_CUDA(cudaMalloc(dst, n * sizeof(float)));
+    IVOSW_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return IVOSW_OK;
+}
+
+// BatchNorm (eval) -> per-channel scale / shift, evaluated in double then rounded once.
+static void fold_bn(const float* g, const float* b, const float* m, const float* v, int n, std::vector<float>& sc,
+                    std::vector<float>& sh) {
+    sc.resize(n); sh.resize(n);
+    for (int i = 0; i < n; ++i) {
+        double s = (double)g[i] / std::sqrt((double)v[i] + (double)BN_EPS);
+        sc[i] = (float)s;
+        sh[i] = (float)((double)b[i] - (double)m[i] * s);
+    }
+}
+
+static int chunk_cap_default() {
+    const char* e = getenv("IVOSW_CHUNK");
+    int v = e ? atoi(e) : 128;
+    return v < 1 ? 1 : v;
+}
+
+// workspace for `cap` scoring units (fp32 NHWC validation path)
+static int ensure_workspace(ivosw_ctx* c, int cap) {
+    int rc;
+    const size_t f = sizeof(float);
+    if ((rc = ensure(c->boxes, (size_t)cap * 4 * f))) return rc;
+    if ((rc = ensure(c->crop, (size_t)cap * ROI * ROI * 4 * f))) return rc;
+    if ((rc = ensure(c->c1, (size_t)cap * 128 * 128 * 64 * f))) return rc;
+    if ((rc = ensure(c->pool, (size_t)cap * 64 * 64 * 64 * f))) return rc;
+    const size_t big = (size_t)cap * 64 * 64 * 256 * f;   // largest block output (res2)
+    if ((rc = ensure(c->actX, big))) return rc;
+    if ((rc = ensure(c->actY, big))) return rc;
+    if ((rc = ensure(c->actDS, big))) return rc;
+    const size_t mid = (size_t)cap * 64 * 64 * 128 * f;   // largest conv1/conv2 output (res3.0.conv1)
+    if ((rc = ensure(c->actT1, mid))) return rc;
+    if ((rc = ensure(c->actT2, mid))) return rc;
+    return IVOSW_OK;
+}
+
+static int keep_probe(ivosw_ctx* c, int which, const float* src, size_t n_floats, cudaStream_t s) {
+    if (!c->probes_on) return IVOSW_OK;
+    int rc;
+    if ((rc = ensure(c->probe_buf[which], n_floats * sizeof(float)))) return rc;
+    IVOSW_CUDA(cudaMemcpyAsync(c->probe_buf[which].p, src, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return IVOSW_OK;
+}
+
+// Scores `n_units` units described by `ua` (ua.u0 is advanced per chunk) into score_dev[0..n_units).
+static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, float* score_dev, float* boxes_dev,
+                        cudaStream_t s) {
+    if (!c->assess_loaded) { set_error("AssessNet weights not loaded"); return IVOSW_ERR_STATE; }
+    int rc;
+    const int cap = std::min(n_units, c->chunk_cap);
+    if ((rc = ensure_workspace(c, cap))) return rc;
+    const int u_first = ua.u0;
+    for (int done = 0; done < n_units; done += cap) {
+        const int B = std::min(cap, n_units - done);
+        ua.u0 = u_first + done;
+        if ((rc = launch_bbox(c, ua, B, H, W, s))) return rc;
+        if ((rc = launch_roi_sample(c, ua, B, H, W, boxes_dev ? boxes_dev + 4 * (size_t)done : (float*)c->boxes.p, s)))
+            return rc;
+        if ((rc = keep_probe(c, 0, (const float*)c->crop.p, (size_t)B * ROI * ROI * 4, s))) return rc;
+        if ((rc = launch_stem(c, B, s))) return rc;
+        if ((rc = keep_probe(c, 1, (const float*)c->pool.p, (size_t)B * 64 * 64 * 64, s))) return rc;
+        const float* x = (const float*)c->pool.p;
+        float* outs[2] = {(float*)c->actX.p, (float*)c->actY.p};
+        int flip = 0, stage_probe = 2;
+        for (size_t li = 0; li < c->layers.size(); ++li) {
+            const ConvLayer& L = c->layers[li];
+            if (L.first_of_block) {
+                if ((rc = launch_conv_simt(c, L, x, nullptr, (float*)c->actT1.p, B, s))) return rc;
+            } else if (L.k == 3) {
+                if ((rc = launch_conv_simt(c, L, (const float*)c->actT1.p, nullptr, (float*)c->actT2.p, B, s))) return rc;
+            } else if (L.is_downsample) {
+                if ((rc = launch_conv_simt(c, L, x, nullptr, (float*)c->actDS.p, B, s))) return rc;
+            } else {  // conv3 + residual + relu -> block output
+                const float* res = L.residual == 2 ? (const float*)c->actDS.p : x;
+                float* y = outs[flip];
+                if ((rc = launch_conv_simt(c, L, (const float*)c->actT2.p, res, y, B, s))) return rc;
+                x = y;
+                flip ^= 1;
+                // a stage ends where the next bottleneck opens with a downsample branch
+                const bool stage_end = (li + 1 == c->layers.size()) ||
+                                       (li + 3 < c->layers.size() && c->layers[li + 3].is_downsample);
+                if (stage_end) {
+                    if ((rc = keep_probe(c, stage_probe, x, (size_t)B * L.out_hw * L.out_hw * L.cout, s))) return rc;
+                    ++stage_probe;
+                }
+            }
+        }
+        if ((rc = launch_gap_fc(c, x, B, score_dev + done, s))) return rc;
+        c->last_chunk_b = B;
+    }
+    return IVOSW_OK;
+}
+
+static int ensure_pinned(ivosw_ctx* c, size_t bytes) {
+    if (c->pinned_small_bytes >= bytes) return IVOSW_OK;
+    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    c->pinned_small = nullptr; c->pinned_small_bytes = 0;
+    IVOSW_CUDA(cudaMallocHost(&c->pinned_small, bytes));
+    c->pinned_small_bytes = bytes;
+    return IVOSW_OK;
+}
+
+}  // namespace ivosw
+
+using namespace ivosw;
+
+extern "C" {
+
+int ivosw_abi_version(void) { return IVOSW_ABI_VERSION; }
+const char* ivosw_last_error(void) { return g_err.c_str(); }
+
+int ivosw_create(int device, int conv_mode, ivosw_ctx** out) {
+    IVOSW_REQUIRE(out != nullptr, "out is NULL");
+    IVOSW_REQUIRE(conv_mode >= 0 && conv_mode <= 2, "conv_mode");
+    int n = 0;
+    IVOSW_CUDA(cudaGetDeviceCount(&n));
+    IVOSW_REQUIRE(device >= 0 && device < n, "device index");
+    IVOSW_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    IVOSW_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("ivosw_b200 is built for sm_100a only; device is ") + prop.name);
+        return IVOSW_ERR_STATE;
+    }
+    ivosw_ctx* c = new ivosw_ctx();
+    c->device = device;
+    c->conv_mode = conv_mode;
+    c->sm_count = prop.multiProcessorCount;
+    c->chunk_cap = chunk_cap_default();
+    c->layers = make_resnet50_layers();
+    *out = c;
+    return IVOSW_OK;
+}
+
+void ivosw_destroy(ivosw_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->brain_params) cudaFree(c->brain_params);
+    if (c->brain_whh_t) cudaFree(c->brain_whh_t);
+    if (c->stem_w) cudaFree(c->stem_w);
+    if (c->stem_scale) cudaFree(c->stem_scale);
+    if (c->stem_shift) cudaFree(c->stem_shift);
+    if (c->fc_w) cudaFree(c->fc_w);
+    for (ConvLayer& L : c->layers) {
+        if (L.w_f32) cudaFree(L.w_f32);
+        if (L.scale) cudaFree(L.scale);
+        if (L.shift) cudaFree(L.shift);
+        if (L.w_hi) cudaFree(L.w_hi);
+        if (L.w_lo) cudaFree(L.w_lo);
+    }
+    DeviceBuffer* bufs[] = {&c->brain_gi, &c->brain_h, &c->brain_state, &c->brain_q, &c->brain_arg, &c->bbox_min,
+                            &c->bbox_max, &c->boxes, &c->crop, &c->c1, &c->pool, &c->actX, &c->actY, &c->actDS,
+                            &c->actT1, &c->actT2, &c->scores, &c->mq, &c->stage_frames, &c->stage_probs};
+    for (DeviceBuffer* b : bufs) release(*b);
+    for (DeviceBuffer& b : c->probe_buf) release(b);
+    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    delete c;
+}
+
+int ivosw_set_conv_mode(ivosw_ctx* c, int conv_mode) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    IVOSW_REQUIRE(conv_mode >= 0 && conv_mode <= 2, "conv_mode");
+    c->conv_mode = conv_mode;
+    return IVOSW_OK;
+}
+
+long long ivosw_launch_count(const ivosw_ctx* c) { return c ? c->launches : 0; }
+
+int ivosw_enable_probes(ivosw_ctx* c, int enable) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    c->probes_on = enable != 0;
+    return IVOSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------- Brain
+int ivosw_brain_load(ivosw_ctx* c, const float* params_host, size_t n_floats) {
+    IVOSW_REQUIRE(c && params_host, "null pointer");
+    IVOSW_REQUIRE(n_floats == IVOSW_BRAIN_NUM_PARAMS, "Brain blob must hold 180993 floats");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(&c->brain_params, params_host, n_floats))) return rc;
+    if ((rc = brain_pack(c))) return rc;
+    c->brain_loaded = true;
+    return IVOSW_OK;
+}
+
+int ivosw_brain_forward(ivosw_ctx* c, const float* state_dev, int N, int T, float* q_dev, int* argmax_dev,
+                        void* stream) {
+    IVOSW_REQUIRE(c && state_dev && q_dev, "null pointer");
+    IVOSW_REQUIRE(N >= 1 && T >= 1 && N <= 65535, "N, T");
+    if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return launch_brain(c, state_dev, N, T, q_dev, argmax_dev, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------------------- AssessNet
+size_t ivosw_assess_blob_floats(void) { return assess_blob_floats(); }
+
+int ivosw_assess_load(ivosw_ctx* c, const float* blob, size_t n_floats) {
+    IVOSW_REQUIRE(c && blob, "null pointer");
+    IVOSW_REQUIRE(n_floats == assess_blob_floats(), "AssessNet blob length");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    int rc;
+    const float* p = blob;
+    for (int i = 0; i < 3; ++i) { c->mean[i] = p[i]; c->stdv[i] = p[3 + i]; }
+    p += 6;
+    {   // stem: [64][7][7][4] -> [(kh,kw,cin)][64]
+        std::vector<float> wt((size_t)196 * 64);
+        for (int co = 0; co < 64; ++co)
+            for (int k = 0; k < 196; ++k) wt[(size_t)k * 64 + co] = p[(size_t)co * 196 + k];
+        if ((rc = upload(&c->stem_w, wt.data(), wt.size()))) return rc;
+        p += (size_t)64 * 196;
+        std::vector<float> sc, sh;
+        fold_bn(p, p + 64, p + 128, p + 192, 64, sc, sh);
+        if ((rc = upload(&c->stem_scale, sc.data(), 64))) return rc;
+        if ((rc = upload(&c->stem_shift, sh.data(), 64))) return rc;
+        p += 256;
+    }
+    for (ConvLayer& L : c->layers) {
+        const size_t nw = (size_t)L.cout * L.k * L.k * L.cin;
+        if ((rc = upload(&L.w_f32, p, nw))) return rc;
+        {   // split-fp16 copy for the tensor-core path: w ~= hi + lo / 2048
+            std::vector<__half> hi(nw), lo(nw);
+            for (size_t i = 0; i < nw; ++i) {
+                __half h = __float2half_rn(p[i]);
+                hi[i] = h;
+                lo[i] = __float2half_rn((p[i] - __half2float(h)) * 2048.0f);
+            }
+            if (!L.w_hi) IVOSW_CUDA(cudaMalloc(&L.w_hi, nw * sizeof(__half)));
+            if (!L.w_lo) IVOSW_CUDA(cudaMalloc(&L.w_lo, nw * sizeof(__half)));
+            IVOSW_CUDA(cudaMemcpy(L.w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
+            IVOSW_CUDA(cudaMemcpy(L.w_lo, lo.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
+        }
+        p += nw;
+        std::vector<float> sc, sh;
+        fold_bn(p, p + L.cout, p + 2 * L.cout, p + 3 * L.cout, L.cout, sc, sh);
+        if ((rc = upload(&L.scale, sc.data(), L.cout))) return rc;
+        if ((rc = upload(&L.shift, sh.data(), L.cout))) return rc;
+        p += 4 * (size_t)L.cout;
+    }
+    if ((rc = upload(&c->fc_w, p, 2048))) return rc;
+    c->fc_b = p[2048];
+    c->assess_loaded = true;
+    return IVOSW_OK;
+}
+
+int ivosw_assess_forward(ivosw_ctx* c, const float* frames_dev, long long frame_stride, const float* prob_dev,
+                         long long prob_stride, int B, int H, int W, float* score_dev, float* boxes_dev,
+                         void* stream) {
+    IVOSW_REQUIRE(c && frames_dev && prob_dev && score_dev, "null pointer");
+    IVOSW_REQUIRE(B >= 1 && H >= 2 && W >= 2, "B, H, W");
+    IVOSW_REQUIRE((long long)H * W < (1ll << 30), "frame too large");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    UnitAddr ua{frames_dev, frame_stride, prob_dev, prob_stride, 0, B, 0};
+    return assess_units(c, ua, B, H, W, score_dev, boxes_dev, (cudaStream_t)stream);
+}
+
+int ivosw_assess_probe(ivosw_ctx* c, int which, float* out_dev, size_t capacity_floats, int* dims4_out,
+                       void* stream) {
+    IVOSW_REQUIRE(c && out_dev, "null pointer");
+    IVOSW_REQUIRE(which >= 0 && which < 6, "which");
+    if (!c->probes_on || !c->probe_buf[which].p) { set_error("probes not enabled / no forward yet"); return IVOSW_ERR_STATE; }
+    static const int C_[6] = {4, 64, 256, 512, 1024, 2048}, HW_[6] = {256, 64, 64, 32, 16, 8};
+    const int B = c->last_chunk_b;
+    const size_t n = (size_t)B * C_[which] * HW_[which] * HW_[which];
+    IVOSW_REQUIRE(capacity_floats >= n, "probe output too small");
+    if (dims4_out) { dims4_out[0] = B; dims4_out[1] = C_[which]; dims4_out[2] = HW_[which]; dims4_out[3] = HW_[which]; }
+    return launch_nhwc_to_nchw(c, (const float*)c->probe_buf[which].p, out_dev, B, HW_[which] * HW_[which], C_[which],
+                               (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------- round
+static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
+                      int t_begin, int t_end, const double* ann_host, double* mq_host, float* scores_host,
+                      float* q_host, int* next_frame, cudaStream_t s) {
+    const int Tl = t_end - t_begin;
+    const long long HW = (long long)H * W;
+    int rc;
+    if ((rc = ensure(c->scores, sizeof(float) * (size_t)Tl * O))) return rc;
+    // mq buffer: [Tl doubles mq][T doubles ann]
+    if ((rc = ensure(c->mq, sizeof(double) * ((size_t)Tl + T)))) return rc;
+    if ((rc = ensure(c->brain_state, sizeof(float) * 2 * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_q, sizeof(float) * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_arg, sizeof(int)))) return rc;
+    const size_t pin_bytes = sizeof(double) * (size_t)(Tl + T) + sizeof(float) * ((size_t)Tl * O + T) + 64;
+    if ((rc = ensure_pinned(c, pin_bytes))) return rc;
+    double* pin_mq = (double*)c->pinned_small;
+    double* pin_ann = pin_mq + Tl;
+    float* pin_scores = (float*)(pin_ann + T);
+    float* pin_q = pin_scores + (size_t)Tl * O;
+    int* pin_arg = (int*)(pin_q + T);
+
+    double* mq_dev = (double*)c->mq.p;
+    double* ann_dev = mq_dev + Tl;
+    const bool full = (t_begin == 0 && t_end == T);
+    memcpy(pin_ann, ann_host, sizeof(double) * T);
+    IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, s));
+
+    UnitAddr ua{frames_dev + (long long)t_begin * 3 * HW, 3 * HW,
+                probs_dev + ((long long)t_begin * (O + 1) + 1) * HW, (long long)(O + 1) * HW, HW, Tl, 0};
+    if ((rc = assess_units(c, ua, Tl * O, H, W, (float*)c->scores.p, nullptr, s))) return rc;
+    if ((rc = launch_object_mean(c, (const float*)c->scores.p, Tl, O, ann_dev + t_begin, mq_dev,
+                                 full ? (float*)c->brain_state.p : nullptr, s)))
+        return rc;
+    if (full && (q_host || next_frame)) {
+        if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+        if ((rc = launch_brain(c, (const float*)c->brain_state.p, 1, T, (float*)c->brain_q.p, (int*)c->brain_arg.p, s)))
+            return rc;
+        IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
+        IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    IVOSW_CUDA(cudaMemcpyAsync(pin_mq, mq_dev, sizeof(double) * Tl, cudaMemcpyDeviceToHost, s));
+    if (scores_host)
+        IVOSW_CUDA(cudaMemcpyAsync(pin_scores, c->scores.p, sizeof(float) * (size_t)Tl * O, cudaMemcpyDeviceToHost, s));
+    IVOSW_CUDA(cudaStreamSynchronize(s));
+    memcpy(mq_host, pin_mq, sizeof(double) * Tl);
+    if (scores_host)   // device layout is [O][Tl]; the reference's mask_quality_pred is [Tl][O]
+        for (int t = 0; t < Tl; ++t)
+            for (int o = 0; o < O; ++o) scores_host[(size_t)t * O + o] = pin_scores[(size_t)o * Tl + t];
+    if (full && q_host) memcpy(q_host, pin_q, sizeof(float) * T);
+    if (full && next_frame) *next_frame = *pin_arg;
+    return IVOSW_OK;
+}
+
+int ivosw_round_device(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
+                       int t_begin, int t_end, const double* ann_host, double* mq_host, float* scores_host,
+                       float* q_host, int* next_frame, void* stream) {
+    IVOSW_REQUIRE(c && frames_dev && probs_dev && ann_host && mq_host, "null pointer");
+    IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 2 && W >= 2, "T, O, H, W");
+    IVOSW_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= T, "frame range");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return round_core(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, ann_host, mq_host, scores_host, q_host,
+                      next_frame, (cudaStream_t)stream);
+}
+
+int ivosw_round_host(ivosw_ctx* c, const float* frames_host, const float* probs_host, int T, int O, int H, int W,
+                     const double* ann_host, double* mq_host, float* scores_host, float* q_host, int* next_frame,
+                     void* stream) {
+    IVOSW_REQUIRE(c && frames_host && probs_host && ann_host && mq_host, "null pointer");
+    IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 2 && W >= 2, "T, O, H, W");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t HW = (size_t)H * W;
+    int rc;
+    if ((rc = ensure(c->stage_frames, sizeof(float) * (size_t)T * 3 * HW))) return rc;
+    if ((rc = ensure(c->stage_probs, sizeof(float) * (size_t)T * (O + 1) * HW))) return rc;
+    IVOSW_CUDA(cudaMemcpyAsync(c->stage_frames.p, frames_host, sizeof(float) * (size_t)T * 3 * HW,
+                               cudaMemcpyHostToDevice, s));
+    IVOSW_CUDA(cudaMemcpyAsync(c->stage_probs.p, probs_host, sizeof(float) * (size_t)T * (O + 1) * HW,
+                               cudaMemcpyHostToDevice, s));
+    return round_core(c, (const float*)c->stage_frames.p, (const float*)c->stage_probs.p, T, O, H, W, 0, T, ann_host,
+                      mq_host, scores_host, q_host, next_frame, s);
+}
+
+int ivosw_agent_action(ivosw_ctx* c, const double* mq_host, const double* ann_host, int T, float* q_host,
+                       int* next_frame, void* stream) {
+    IVOSW_REQUIRE(c && mq_host && ann_host, "null pointer");
+    IVOSW_REQUIRE(T >= 1, "T");
+    if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure(c->brain_state, sizeof(float) * 2 * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_q, sizeof(float) * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_arg, sizeof(int)))) return rc;
+    if ((rc = ensure_pinned(c, sizeof(float) * 3 * (size_t)T + 64))) return rc;
+    float* pin_state = (float*)c->pinned_small;
+    float* pin_q = pin_state + 2 * (size_t)T;
+    int* pin_arg = (int*)(pin_q + T);
+    for (int t = 0; t < T; ++t) {   // torch.Tensor(state[None]) : float64 -> float32 (agent.py:176)
+        pin_state[2 * t] = (float)mq_host[t];
+        pin_state[2 * t + 1] = (float)ann_host[t];
+    }
+    IVOSW_CUDA(cudaMemcpyAsync(c->brain_state.p, pin_state, sizeof(float) * 2 * T, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_brain(c, (const float*)c->brain_state.p, 1, T, (float*)c->brain_q.p, (int*)c->brain_arg.p, s)))
+        return rc;
+    IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
+    IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IVOSW_CUDA(cudaStreamSynchronize(s));
+    if (q_host) memcpy(q_host, pin_q, sizeof(float) * T);
+    if (next_frame) *next_frame = *pin_arg;
+    return IVOSW_OK;
+}
+
+// -------------------------------------------------------------------------------------- MANet tail
+int ivosw_manet_tail(ivosw_ctx* c, const float* logits_dev, int T, int C, int h, int w, int H, int W,
+                     float* masks_dev, float* all_p_dev, void* stream) {
+    IVOSW_REQUIRE(c && logits_dev, "null pointer");
+    IVOSW_REQUIRE(T >= 1 && C >= 1 && C <= 16 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "T, C (<= 16), h, w, H, W");
+    IVOSW_REQUIRE(T <= 65535 && H <= 65535, "T, H <= 65535");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return launch_manet_tail(c, logits_dev, T, C, h, w, H, W, masks_dev, all_p_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

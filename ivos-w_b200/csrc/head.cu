@@ -1,0 +1,66 @@
+// Tail of AssessNet.forward (models/assessment.py:179-180): avg_pool2d(r5, 8) -> fc1 (2048 -> 1),
+// and the per-frame glue of recommend_frame (utils/utils_agent.py:120-121): float64 mean over the
+// objects and packing of the Brain input state [mask_quality, annotated_count] as fp32.
+#include "ivosw_internal.h"
+
+namespace ivosw {
+
+// r5: [B][64][2048] NHWC fp32.  One CTA per sample.
+__global__ void __launch_bounds__(256) gap_fc_kernel(const float* __restrict__ r5, const float* __restrict__ fcw,
+                                                     float fcb, float* __restrict__ score) {
+    const int b = blockIdx.x;
+    const float* x = r5 + (long long)b * 64 * 2048;
+    float part = 0.f;
+    for (int ch = threadIdx.x; ch < 2048; ch += 256) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int p = 0; p < 64; ++p) s += x[p * 2048 + ch];
+        part = fmaf(s * (1.0f / 64.0f), __ldg(fcw + ch), part);
+    }
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i];
+        score[b] = t + fcb;
+    }
+}
+
+int launch_gap_fc(ivosw_ctx* c, const float* r5, int B, float* scores, cudaStream_t s) {
+    gap_fc_kernel<<<B, 256, 0, s>>>(r5, c->fc_w, c->fc_b, scores);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+// scores: [O][T] fp32 (object-major, as the per-object AssessNet calls produce them).
+// mq[t] = float64 mean over objects (numpy .mean(1) of a float64 array holding fp32 values);
+// state[t] = (float(mq[t]), float(ann[t]))  — torch.Tensor(state[None]) casts to fp32 (agent.py:176).
+__global__ void object_mean_kernel(const float* __restrict__ scores, int T, int O, const double* __restrict__ ann,
+                                   double* __restrict__ mq, float* __restrict__ state) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    // numpy's pairwise/sequential add for tiny O: plain left-to-right float64 sum, then divide
+    double s = 0.0;
+    for (int o = 0; o < O; ++o) s += (double)scores[(long long)o * T + t];
+    double m = s / (double)O;
+    mq[t] = m;
+    if (state) {
+        state[2 * t + 0] = (float)m;
+        state[2 * t + 1] = (float)ann[t];
+    }
+}
+
+int launch_object_mean(ivosw_ctx* c, const float* scores, int T, int O, const double* ann_dev, double* mq_dev,
+                       float* state_dev, cudaStream_t s) {
+    object_mean_kernel<<<(T + 127) / 128, 128, 0, s>>>(scores, T, O, ann_dev, mq_dev, state_dev);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+}  // namespace ivosw

@@ -1,0 +1,141 @@
+// Internal declarations shared by the CUDA translation units behind include/ivosw_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ivosw_b200.h"
+
+namespace ivosw {
+
+constexpr int ROI = 256;           // models/assessment.py:170 dst_size
+constexpr float BN_EPS = 1e-5f;    // torch BatchNorm2d default
+constexpr int BRAIN_H = 128;       // models/agent.py:14 hidden_channels
+constexpr int BRAIN_G = 4 * BRAIN_H;
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define IVOSW_CUDA(call)                                                         \
+    do {                                                                         \
+        cudaError_t _e = (call);                                                 \
+        if (_e != cudaSuccess) return ::ivosw::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define IVOSW_REQUIRE(cond, msg)                                  \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::ivosw::set_error(std::string("invalid argument: ") + (msg)); \
+            return IVOSW_ERR_INVALID;                             \
+        }                                                         \
+    } while (0)
+
+// One convolution of res2..res5 (mirrors ivosw/arch.py::resnet50_convs).
+struct ConvLayer {
+    int cin, cout, k, stride, pad;
+    int in_hw, out_hw;
+    bool relu;
+    int residual;         // 0 none, 1 identity (block input), 2 downsample output
+    bool is_downsample;
+    bool first_of_block;  // conv1 of a bottleneck: its input is the block input
+    // device parameters
+    float* w_f32 = nullptr;    // [cout][k][k][cin]
+    float* scale = nullptr;    // gamma / sqrt(var + eps)
+    float* shift = nullptr;    // beta - mean * scale
+    __half* w_hi = nullptr;    // tensor-core path: fp16 head of the weight, [cout][k*k*cin]
+    __half* w_lo = nullptr;    //                   fp16((w - hi) * 2048)
+};
+
+std::vector<ConvLayer> make_resnet50_layers();
+
+// Where the inputs of scoring unit u = (object o, frame f) live: u = u0 + local index, f = u % nF,
+// o = u / nF.  One AssessNet.forward call is nF = B, obj_stride = 0; a whole round is nF = frames of
+// the shard with obj_stride = H*W walking over all_P[:, 1:].
+struct UnitAddr {
+    const float* frames; long long frame_stride;
+    const float* prob; long long prob_stride; long long obj_stride;
+    int nF; int u0;
+    __host__ __device__ const float* frame(int local) const {
+        int u = u0 + local; return frames + (long long)(u % nF) * frame_stride;
+    }
+    __host__ __device__ const float* prob_plane(int local) const {
+        int u = u0 + local; return prob + (long long)(u % nF) * prob_stride + (long long)(u / nF) * obj_stride;
+    }
+};
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace ivosw
+
+struct ivosw_ctx {
+    int device = 0;
+    int conv_mode = 0;
+    int sm_count = 148;
+    long long launches = 0;
+
+    // Brain
+    bool brain_loaded = false;
+    float* brain_params = nullptr;   // canonical order, see header
+    float* brain_whh_t = nullptr;    // weight_hh transposed/packed for the recurrent kernel
+    ivosw::DeviceBuffer brain_gi, brain_h, brain_state, brain_q, brain_arg;
+
+    // AssessNet
+    bool assess_loaded = false;
+    float* stem_w = nullptr;         // [196][64]: (kh,kw,cin) x cout
+    float* stem_scale = nullptr;
+    float* stem_shift = nullptr;
+    float mean[3], stdv[3];
+    float* fc_w = nullptr;           // 2048
+    float fc_b = 0.f;
+    std::vector<ivosw::ConvLayer> layers;
+
+    // workspace (grown on demand, per chunk of `chunk_cap` samples)
+    int chunk_cap = 0;
+    ivosw::DeviceBuffer bbox_min, bbox_max, boxes, crop, c1, pool, actX, actY, actDS, actT1, actT2, scores, mq;
+    // what the probe entry point can read back (valid for the last chunk processed)
+    bool probes_on = false;
+    int last_chunk_b = 0;
+    ivosw::DeviceBuffer probe_buf[6];   // fp32 NHWC copies: crop, pool, r2, r3, r4, r5
+
+    // host-staged rounds
+    ivosw::DeviceBuffer stage_frames, stage_probs;
+    void* pinned_small = nullptr;    // small pinned scratch for D2H results
+    size_t pinned_small_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+};
+
+namespace ivosw {
+
+int ensure(DeviceBuffer& b, size_t bytes);
+void release(DeviceBuffer& b);
+
+// ---- roi.cu
+int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s);
+int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, cudaStream_t s);
+// ---- stem.cu
+int launch_stem(ivosw_ctx* c, int B, cudaStream_t s);
+// ---- conv_simt.cu
+int launch_conv_simt(ivosw_ctx* c, const ConvLayer& L, const float* in, const float* residual, float* out,
+                     int B, cudaStream_t s);
+// ---- head.cu
+int launch_gap_fc(ivosw_ctx* c, const float* r5, int B, float* scores, cudaStream_t s);
+int launch_object_mean(ivosw_ctx* c, const float* scores, int T, int O, const double* ann_dev, double* mq_dev,
+                       float* state_dev, cudaStream_t s);
+// ---- brain.cu
+int brain_pack(ivosw_ctx* c);
+int launch_brain(ivosw_ctx* c, const float* state, int N, int T, float* q, int* argmax, cudaStream_t s);
+// ---- manet_tail.cu
+int launch_manet_tail(ivosw_ctx* c, const float* logits, int T, int C, int h, int w, int H, int W, float* masks,
+                      float* all_p, cudaStream_t s);
+// ---- probe helper (NHWC -> NCHW)
+int launch_nhwc_to_nchw(ivosw_ctx* c, const float* in, float* out, int B, int HW, int C, cudaStream_t s);
+
+}  // namespace ivosw

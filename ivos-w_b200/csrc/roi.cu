@@ -1,0 +1,231 @@
+// ROI stage of AssessNet.forward (models/assessment.py:165-174), entirely on device:
+//   bbox_kernel        tm = (tp > 0.5); per-plane min/max row/col        (:165, all2yxhw :115-125)
+//   roi_sample_kernel  all2yxhw box arithmetic (:128-157), theta (:77-93), forward affine grid
+//                      (:104-105), bilinear zero-padded sampling of RGB and prob (:173-174) and the
+//                      encoder's input normalisation (:47), written as one 4-channel NHWC crop.
+// The reference does the bbox on the host with numpy after a device->host copy of the mask and
+// also builds an inverse grid nobody reads (:95-107); both are dropped here (SURVEY A.Q4).
+//
+// HBM-bound.  Algorithmic bytes per (frame, object): H*W*4 read by bbox_kernel; the ROI footprint
+// of 4 planes read (<= 4*H*W*4) + 4*256*256*4 written by roi_sample_kernel.
+#include "ivosw_internal.h"
+
+namespace ivosw {
+
+// ------------------------------------------------------------------------------------------------
+// bbox: every CTA scans a contiguous slice of one probability plane with 128-bit loads and folds its
+// result into the plane's (ymin, xmin) / (ymax, xmax) with integer atomics.
+// ------------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256) bbox_kernel(UnitAddr ua, int HW, int W, int per_cta, int2* __restrict__ mn,
+                                                   int2* __restrict__ mx) {
+    const int b = blockIdx.y;
+    const float* plane = ua.prob_plane(b);
+    int start = blockIdx.x * per_cta;
+    int end = min(HW, start + per_cta);
+    int ymin = 0x7fffffff, xmin = 0x7fffffff, ymax = -1, xmax = -1;
+    if (VEC4) {
+        // start / per_cta are multiples of 4 and the plane is 16-byte aligned
+        for (int i = start + threadIdx.x * 4; i < end; i += blockDim.x * 4) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(plane + i));
+            bool any = (v.x > 0.5f) | (v.y > 0.5f) | (v.z > 0.5f) | (v.w > 0.5f);
+            if (any) {
+                float vv[4] = {v.x, v.y, v.z, v.w};
+                int y = i / W, x = i - y * W;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (vv[j] > 0.5f) {  // strict: (tp > 0.5) then >= 0.49 on {0,1}  (SURVEY A.Q2)
+                        ymin = min(ymin, y); ymax = max(ymax, y);
+                        xmin = min(xmin, x); xmax = max(xmax, x);
+                    }
+                    if (++x == W) { x = 0; ++y; }
+                }
+            }
+        }
+    } else {
+        for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
+            if (__ldg(plane + i) > 0.5f) {
+                int y = i / W, x = i - y * W;
+                ymin = min(ymin, y); ymax = max(ymax, y);
+                xmin = min(xmin, x); xmax = max(xmax, x);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && ymax >= 0) {
+        atomicMin(&mn[b].x, ymin); atomicMin(&mn[b].y, xmin);
+        atomicMax(&mx[b].x, ymax); atomicMax(&mx[b].y, xmax);
+    }
+}
+
+int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s) {
+    int rc;
+    if ((rc = ensure(c->bbox_min, sizeof(int2) * (size_t)B))) return rc;
+    if ((rc = ensure(c->bbox_max, sizeof(int2) * (size_t)B))) return rc;
+    IVOSW_CUDA(cudaMemsetAsync(c->bbox_min.p, 0x7f, sizeof(int2) * (size_t)B, s));
+    IVOSW_CUDA(cudaMemsetAsync(c->bbox_max.p, 0xff, sizeof(int2) * (size_t)B, s));
+    const int HW = H * W;
+    // enough CTAs to cover the machine a few times over, each with >= 16 KB of plane
+    int ctas = max(1, min((HW + 4095) / 4096, (8 * c->sm_count + B - 1) / B));
+    int per_cta = (((HW + ctas - 1) / ctas) + 3) & ~3;
+    ctas = (HW + per_cta - 1) / per_cta;
+    bool vec = ((reinterpret_cast<uintptr_t>(ua.prob) & 15) == 0) && (ua.prob_stride % 4 == 0) &&
+               (ua.obj_stride % 4 == 0) && (HW % 4 == 0);
+    dim3 grid(ctas, B);
+    if (vec)
+        bbox_kernel<true><<<grid, 256, 0, s>>>(ua, HW, W, per_cta, (int2*)c->bbox_min.p, (int2*)c->bbox_max.p);
+    else
+        bbox_kernel<false><<<grid, 256, 0, s>>>(ua, HW, W, per_cta, (int2*)c->bbox_min.p, (int2*)c->bbox_max.p);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// all2yxhw box arithmetic, exactly as numpy evaluates it (int64 / float64, then float32 cast).
+// ------------------------------------------------------------------------------------------------
+__device__ inline void box_from_minmax(int2 mn, int2 mx, int H, int W, float* yxhw) {
+    long long ymin, ymax, xmin, xmax;
+    if (mx.x < 0) {  // empty mask -> whole frame, upper bound H (not H-1)   (:119-122, SURVEY A.Q3)
+        ymin = 0; ymax = H; xmin = 0; xmax = W;
+    } else {
+        ymin = mn.x; ymax = mx.x; xmin = mn.y; xmax = mx.y;
+    }
+    if (ymax - ymin < 128) {  // :128-131   int(res / 2) truncates
+        double res = 128.0 - (double)(ymax - ymin);
+        long long g = (long long)(res / 2.0);
+        ymin -= g; ymax += g;
+    }
+    if (xmax - xmin < 128) {  // :133-136
+        double res = 128.0 - (double)(xmax - xmin);
+        long long g = (long long)(res / 2.0);
+        xmin -= g; xmax += g;
+    }
+    const double orig_h = (double)(ymax - ymin + 1), orig_w = (double)(xmax - xmin + 1);  // :141-142
+    const double k = (1.5 - 1.0) / 2.0;                                                   // scale = 1.5
+    double fymin = fmax(-5.0, (double)ymin - k * orig_h);                                  // :144-149
+    double fymax = fmin((double)(H + 5), (double)ymax + k * orig_h);
+    double fxmin = fmax(-5.0, (double)xmin - k * orig_w);
+    double fxmax = fmin((double)(W + 5), (double)xmax + k * orig_w);
+    yxhw[0] = (float)((fymax + fymin) / 2.0);                                              // :152-157
+    yxhw[1] = (float)((fxmax + fxmin) / 2.0);
+    yxhw[2] = (float)(fymax - fymin + 1.0);
+    yxhw[3] = (float)(fxmax - fxmin + 1.0);
+}
+
+// at::linspace(-1, 1, 256)[i] as torch's CPU kernel evaluates it (fp32 step, one FMA per half);
+// pinned bit-exact in tests/test_oracle_golden.py.
+__device__ inline float lin256(int i) {
+    const float step = 2.0f / 255.0f;
+    return (i < ROI / 2) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(ROI - 1 - i), 1.0f);
+}
+
+constexpr int ROI_ROWS_PER_CTA = 8;
+
+__global__ void __launch_bounds__(256) roi_sample_kernel(UnitAddr ua, int H, int W, const int2* __restrict__ mn,
+                                                         const int2* __restrict__ mx, float3 mean, float3 stdv,
+                                                         float* __restrict__ boxes, float4* __restrict__ crop) {
+    __shared__ float th[4];
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        float r[4];
+        box_from_minmax(mn[b], mx[b], H, W, r);
+        if (blockIdx.x == 0 && boxes) {
+            boxes[4 * b + 0] = r[0]; boxes[4 * b + 1] = r[1]; boxes[4 * b + 2] = r[2]; boxes[4 * b + 3] = r[3];
+        }
+        // get_ROI_grid (:77-93), fp32 tensor arithmetic, scale = 1.0; no FMA contraction
+        float rh = __fmul_rn(1.0f, r[2]), rw = __fmul_rn(1.0f, r[3]);
+        float ymin = __fsub_rn(r[0], __fdiv_rn(rh, 2.f)), ymax = __fadd_rn(r[0], __fdiv_rn(rh, 2.f));
+        float xmin = __fsub_rn(r[1], __fdiv_rn(rw, 2.f)), xmax = __fadd_rn(r[1], __fdiv_rn(rw, 2.f));
+        float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+        th[0] = __fdiv_rn(__fsub_rn(xmax, xmin), wm1);                        // theta[0,0]
+        th[1] = __fdiv_rn(__fsub_rn(__fadd_rn(xmin, xmax), wm1), wm1);        // theta[0,2]
+        th[2] = __fdiv_rn(__fsub_rn(ymax, ymin), hm1);                        // theta[1,1]
+        th[3] = __fdiv_rn(__fsub_rn(__fadd_rn(ymin, ymax), hm1), hm1);        // theta[1,2]
+    }
+    __syncthreads();
+    const int ox = threadIdx.x;
+    // affine_grid: one rounded multiply, one rounded add (bit-exact vs torch CPU)
+    const float gx = __fadd_rn(__fmul_rn(th[0], lin256(ox)), th[1]);
+    // grid_sample unnormalise, align_corners=True: ((g + 1) / 2) * (size - 1)
+    const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
+    const float fx0 = floorf(ix);
+    const int x0 = (int)fx0, x1 = x0 + 1;
+    const float wx1 = __fsub_rn(ix, fx0), wx0 = __fsub_rn(1.f, wx1);  // ATen: w = x - floor(x); e = 1 - w
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+    const float* fr = ua.frame(b);
+    const float* pp = ua.prob_plane(b);
+    const long long HW = (long long)H * W;
+#pragma unroll 2
+    for (int r = 0; r < ROI_ROWS_PER_CTA; ++r) {
+        const int oy = blockIdx.x * ROI_ROWS_PER_CTA + r;
+        const float gy = __fadd_rn(__fmul_rn(th[2], lin256(oy)), th[3]);
+        const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+        const float fy0 = floorf(iy);
+        const int y0 = (int)fy0, y1 = y0 + 1;
+        const float wy1 = __fsub_rn(iy, fy0), wy0 = __fsub_rn(1.f, wy1);
+        const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+        const float w_nw = __fmul_rn(wx0, wy0), w_ne = __fmul_rn(wx1, wy0);
+        const float w_sw = __fmul_rn(wx0, wy1), w_se = __fmul_rn(wx1, wy1);
+        const int o_nw = y0 * W + x0, o_ne = o_nw + 1, o_sw = o_nw + W, o_se = o_sw + 1;
+        float out[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const float* pl = (ch < 3) ? (fr + ch * HW) : pp;
+            float a = (vy0 & vx0) ? __ldg(pl + o_nw) : 0.f;
+            float bb = (vy0 & vx1) ? __ldg(pl + o_ne) : 0.f;
+            float cc = (vy1 & vx0) ? __ldg(pl + o_sw) : 0.f;
+            float d = (vy1 & vx1) ? __ldg(pl + o_se) : 0.f;
+            float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, w_nw), __fmul_rn(bb, w_ne)), __fmul_rn(cc, w_sw)),
+                                __fmul_rn(d, w_se));
+            out[ch] = v;
+        }
+        // Encoder.forward :47  f = (in_f - mean) / std   (applied after sampling, as the reference does)
+        out[0] = __fdiv_rn(__fsub_rn(out[0], mean.x), stdv.x);
+        out[1] = __fdiv_rn(__fsub_rn(out[1], mean.y), stdv.y);
+        out[2] = __fdiv_rn(__fsub_rn(out[2], mean.z), stdv.z);
+        crop[((long long)b * ROI + oy) * ROI + ox] = make_float4(out[0], out[1], out[2], out[3]);
+    }
+}
+
+int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, cudaStream_t s) {
+    dim3 grid(ROI / ROI_ROWS_PER_CTA, B);
+    roi_sample_kernel<<<grid, 256, 0, s>>>(ua, H, W, (const int2*)c->bbox_min.p,
+                                           (const int2*)c->bbox_max.p,
+                                           make_float3(c->mean[0], c->mean[1], c->mean[2]),
+                                           make_float3(c->stdv[0], c->stdv[1], c->stdv[2]), boxes_out,
+                                           (float4*)c->crop.p);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe helper: NHWC -> NCHW (parity tests read intermediates in the reference's layout)
+// ------------------------------------------------------------------------------------------------
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int HW,
+                                    int C) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int cc = (int)(i % C);
+    long long r = i / C;
+    int p = (int)(r % HW);
+    long long b = r / HW;
+    out[(b * C + cc) * HW + p] = in[i];
+}
+
+int launch_nhwc_to_nchw(ivosw_ctx* c, const float* in, float* out, int B, int HW, int C, cudaStream_t s) {
+    long long total = (long long)B * HW * C;
+    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, total, HW, C);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+}  // namespace ivosw

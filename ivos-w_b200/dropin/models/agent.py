@@ -1,0 +1,132 @@
+"""Drop-in for the reference's ``models/agent.py`` (Brain 13-64, Agent 67-237).
+
+Same class names, constructor arguments, ``state_dict`` keys and ``forward`` /
+``action`` signatures; the Q-network arithmetic runs in the CUDA library
+(ivos-w_b200/csrc/brain.cu) through the C ABI.  The modules hold ordinary
+``nn.Parameter``s only so that ``load_state_dict(strict=True)`` and
+``utils.misc.load_agent_checkpoint`` keep working; the parameters are re-packed
+and uploaded to the library whenever they change.  There is no PyTorch forward:
+calling these modules without a CUDA device raises.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from ivosw import arch
+from ivosw.engine import get_engine
+
+
+class Brain(nn.Module):
+    def __init__(self, lstm_input_channels=128, hidden_channels=128, num_fc_concat=128):
+        super(Brain, self).__init__()
+        if (lstm_input_channels, hidden_channels, num_fc_concat) != (128, 128, 128):
+            raise NotImplementedError("the CUDA Q-network is built for the reference's 128/128/128 Brain")
+        self.input_channels = lstm_input_channels
+        self.hidden_channels = hidden_channels
+        self.num_fc_concat = num_fc_concat
+        # parameter containers with the reference's names and default initialisation (agent.py:19-29)
+        self.encoder_fc1 = nn.Linear(2, 128)
+        self.encoder_fc2 = nn.Linear(128, self.input_channels)
+        self.lstm_cell = nn.LSTMCell(self.input_channels, self.hidden_channels, False)
+        self.decoder_fc1 = nn.Linear(2 * self.hidden_channels, self.num_fc_concat)
+        self.decoder_fc2 = nn.Linear(self.num_fc_concat, 1)
+        self._uploaded = None
+
+    def _sync(self, engine):
+        sd = self.state_dict()
+        stamp = tuple((sd[k].data_ptr(), sd[k]._version) for k, _ in arch.BRAIN_PARAMS) + (id(engine),)
+        if stamp != self._uploaded:
+            engine.load_brain(sd)
+            self._uploaded = stamp
+
+    def forward(self, input):
+        """input: N x T x 2 -> N x T  (agent.py:33-64)."""
+        if not input.is_cuda:
+            raise RuntimeError("ivosw_b200 Brain runs on CUDA only (no CPU fallback); got a %s tensor" % input.device)
+        engine = get_engine(input.device)
+        self._sync(engine)
+        return engine.brain_forward(input)
+
+    def q_and_argmax(self, input):
+        engine = get_engine(input.device)
+        self._sync(engine)
+        return engine.brain_forward(input, want_argmax=True)
+
+
+class Agent(nn.Module):
+    def __init__(self, device, cfg):
+        super(Agent, self).__init__()
+        self.cfg = cfg
+        self.device = device
+        self.memory_size = self.cfg.agent.memory_size
+        self.GAMMA = self.cfg.agent.gamma
+        self.EPS_START = self.cfg.agent.eps_start
+        self.EPS_END = self.cfg.agent.eps_end
+        self.EPS_DECAY = self.cfg.agent.eps_decay
+        self.steps_done = 0
+        self.update_rate = self.cfg.agent.update_rate
+        self.subset = self.cfg.data.subset
+        from models.momory_pool import ReplayMemory
+        self.memory_pool = ReplayMemory(self.memory_size)
+
+        self.policy_net = Brain()
+        self.target_net = Brain()
+        self.target_net.load_state_dict(self.policy_net.state_dict())
+        self.policy_net.to(self.device)
+        self.target_net.to(self.device)
+
+        self.loss = []
+        self.loss_position = 0
+        self.loss_capacity = 32
+        self.loss_avg = 0
+        self.optimizer = optim.Adam(self.policy_net.parameters(), lr=cfg.agent.lr,
+                                    weight_decay=cfg.agent.weight_decay)
+
+    def action(self, state, verbose=True):
+        """agent.py:168-196.  Side effects kept: steps_done += 1 and exactly one random.random()
+        draw per call (SURVEY A.Q6) so the global RNG stream stays aligned with the reference."""
+        self.steps_done += 1
+        if not self.cfg.phase == 'train':
+            eps_threshold = 0
+        else:
+            eps_threshold = self.EPS_END + (self.EPS_START - self.EPS_END) * \
+                math.exp(-0.5 * self.steps_done / self.EPS_DECAY)
+        state = np.asarray(state)
+        rand_flag = random.random()
+        if rand_flag > eps_threshold:
+            if verbose:
+                print(f"step:{self.steps_done}, rand_flag:{rand_flag:.4f}, eps_threshold:{eps_threshold:.4f}, "
+                      f"frame index was selected by agent")
+            engine = get_engine(self.device)
+            self.policy_net._sync(engine)
+            action, _ = engine.agent_action(state[:, 0], state[:, 1])
+            return np.int64(action)
+        else:
+            if verbose:
+                print(f"step:{self.steps_done}, rand_flag:{rand_flag:.4f}, eps_threshold:{eps_threshold:.4f}, "
+                      f"frame index was selected randomly")
+            action_idx = np.array(range(state.shape[0]))
+            return random.choice(action_idx)
+
+    def update_agent(self, sample):
+        raise NotImplementedError(
+            "Agent.update_agent (Double-DQN training step, agent.py:103-166) is a 'next' row of the scope "
+            "table (SURVEY.md §8(f) rank 2) and is not built yet; the inference path never calls it.")
+
+    def set_train(self):
+        self.policy_net.train()
+        self.target_net.train()
+
+    def set_eval(self):
+        self.policy_net.eval()
+        self.target_net.eval()
+
+    def memory(self, *args):
+        self.memory_pool.push(*args[:-1])
+
+    def get_avg_loss(self):
+        return self.loss_avg

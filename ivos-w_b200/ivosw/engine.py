@@ -1,0 +1,246 @@
+"""Engine: a thin, torch-aware wrapper around one ``ivosw_ctx`` (one per GPU).
+
+PyTorch is used here only for device memory, streams and (in ``dist.py``)
+``torch.distributed``; all arithmetic happens in the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import arch
+from ._lib import (BRAIN_NUM_PARAMS, CONV_SIMT_FP32, CONV_TC_FP16X1, CONV_TC_FP16X3, check, lib)
+
+CONV_MODES = {"simt_fp32": CONV_SIMT_FP32, "tc_fp16x3": CONV_TC_FP16X3, "tc_fp16x1": CONV_TC_FP16X1}
+DEFAULT_CONV_MODE = "simt_fp32"
+
+
+def pack_brain(sd):
+    """Brain.state_dict() -> flat fp32 array in the order include/ivosw_b200.h documents."""
+    parts = []
+    for key, shape in arch.BRAIN_PARAMS:
+        t = sd[key].detach().to("cpu", torch.float32).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("Brain parameter %s has shape %s, expected %s" % (key, tuple(t.shape), shape))
+        parts.append(t.reshape(-1).numpy())
+    out = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+    assert out.size == BRAIN_NUM_PARAMS
+    return out
+
+
+def pack_assess(sd):
+    """AssessNet.state_dict() -> flat fp32 blob (see ivosw_assess_load).  Weights go OIHW -> OHWI."""
+    def f(key):
+        return sd[key].detach().to("cpu", torch.float32)
+
+    parts = [f("Encoder.mean").reshape(-1), f("Encoder.std").reshape(-1)]
+    stem = torch.cat([f("Encoder.conv1.weight"), f("Encoder.conv1_p.weight")], 1)       # 64 x 4 x 7 x 7
+    parts.append(stem.permute(0, 2, 3, 1).reshape(-1))
+    for s in ("weight", "bias", "running_mean", "running_var"):
+        parts.append(f("Encoder.bn1." + s))
+    for c in arch.resnet50_convs():
+        w = f(c.name + ".weight")
+        if tuple(w.shape) != (c.cout, c.cin, c.k, c.k):
+            raise ValueError("%s.weight has shape %s" % (c.name, tuple(w.shape)))
+        parts.append(w.permute(0, 2, 3, 1).reshape(-1))
+        for s in ("weight", "bias", "running_mean", "running_var"):
+            parts.append(f(c.bn + "." + s))
+    parts += [f("fc1.weight").reshape(-1), f("fc1.bias").reshape(-1)]
+    out = np.ascontiguousarray(torch.cat([p.contiguous().reshape(-1) for p in parts]).numpy(), dtype=np.float32)
+    if out.size != lib.ivosw_assess_blob_floats():
+        raise ValueError("AssessNet blob has %d floats, library expects %d" % (out.size, lib.ivosw_assess_blob_floats()))
+    return out
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """One CUDA context of the scoring library on ``device`` (int or torch.device)."""
+
+    def __init__(self, device=0, conv_mode=DEFAULT_CONV_MODE):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ivosw_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(device if not isinstance(device, int) else "cuda:%d" % device)
+        if dev.type != "cuda":
+            raise RuntimeError("ivosw_b200 runs on CUDA devices only, got %r" % (device,))
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        torch.cuda.init()
+        torch.zeros(1, device=self.device)     # make sure torch's primary context exists (shared with the library)
+        h = C.c_void_p()
+        check(lib.ivosw_create(self.device.index, CONV_MODES[conv_mode], C.byref(h)))
+        self._h = h
+        self.conv_mode = conv_mode
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ivosw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration
+    def set_conv_mode(self, mode):
+        check(lib.ivosw_set_conv_mode(self._h, CONV_MODES[mode]))
+        self.conv_mode = mode
+
+    @property
+    def launch_count(self):
+        return int(lib.ivosw_launch_count(self._h))
+
+    def load_brain(self, sd):
+        blob = pack_brain(sd)
+        check(lib.ivosw_brain_load(self._h, _np_ptr(blob), blob.size))
+
+    def load_assess(self, sd):
+        blob = pack_assess(sd)
+        check(lib.ivosw_assess_load(self._h, _np_ptr(blob), blob.size))
+
+    # ------------------------------------------------------------------ Brain (models/agent.py:33)
+    def brain_forward(self, state, want_argmax=False):
+        """state: N x T x 2 CUDA fp32 tensor -> Q (N x T) [, argmax (N) int32]."""
+        state = self._dev32(state)
+        N, T, P = state.shape
+        if P != 2:
+            raise ValueError("Brain input must be N x T x 2")
+        q = torch.empty((N, T), device=self.device, dtype=torch.float32)
+        am = torch.empty((N,), device=self.device, dtype=torch.int32) if want_argmax else None
+        check(lib.ivosw_brain_forward(self._h, _ptr(state), N, T, _ptr(q), _ptr(am), _stream(self.device)))
+        return (q, am) if want_argmax else q
+
+    # ------------------------------------------------------------------ AssessNet (models/assessment.py:164)
+    def assess_forward(self, tf, tp, want_boxes=False):
+        """tf: B x 3 x H x W, tp: B x H x W (CUDA fp32; tp may be a strided slice such as
+        all_P[:, i+1]).  Returns scores (B,) [, boxes (B, 4)]."""
+        tf = self._dev32(tf)
+        B, Cc, H, W = tf.shape
+        if Cc != 3:
+            raise ValueError("tf must be B x 3 x H x W")
+        if tp.device != self.device or tp.dtype != torch.float32:
+            tp = tp.to(self.device, torch.float32)
+        if tuple(tp.shape) != (B, H, W):
+            raise ValueError("tp must be B x H x W matching tf")
+        if tp.stride(2) != 1 or tp.stride(1) != W:
+            tp = tp.contiguous()
+        pstride = tp.stride(0) if B > 1 else H * W
+        scores = torch.empty((B,), device=self.device, dtype=torch.float32)
+        boxes = torch.empty((B, 4), device=self.device, dtype=torch.float32) if want_boxes else None
+        check(lib.ivosw_assess_forward(self._h, _ptr(tf), 3 * H * W, _ptr(tp), pstride, B, H, W, _ptr(scores),
+                                       _ptr(boxes), _stream(self.device)))
+        return (scores, boxes) if want_boxes else scores
+
+    def enable_probes(self, on=True):
+        check(lib.ivosw_enable_probes(self._h, 1 if on else 0))
+
+    def probe(self, which):
+        """0 crop, 1 pool, 2..5 r2..r5 of the last assess chunk, as an NCHW fp32 CUDA tensor."""
+        Cn = (4, 64, 256, 512, 1024, 2048)[which]
+        hw = (256, 64, 64, 32, 16, 8)[which]
+        cap = 128 * Cn * hw * hw
+        dims = (C.c_int * 4)()
+        buf = torch.empty((cap,), device=self.device, dtype=torch.float32)
+        check(lib.ivosw_assess_probe(self._h, which, _ptr(buf), cap, dims, _stream(self.device)))
+        n, c, h, w = [int(v) for v in dims]
+        return buf[: n * c * h * w].view(n, c, h, w)
+
+    # ------------------------------------------------------------------ round (utils/utils_agent.py:111-122)
+    def round_device(self, all_F, all_P, annotated_counts, t_begin=0, t_end=None, want_scores=False,
+                     want_action=True):
+        """all_F: T x 3 x H x W, all_P: T x (O+1) x H x W CUDA fp32 tensors.
+        Returns dict(mask_quality float64[t_end-t_begin], scores fp32[.., O] or None, q fp32[T] or None,
+        next_frame int or None).  q / next_frame only for the full range."""
+        all_F = self._dev32(all_F)
+        all_P = self._dev32(all_P)
+        T, _, H, W = all_F.shape
+        O = all_P.shape[1] - 1
+        t_end = T if t_end is None else t_end
+        full = t_begin == 0 and t_end == T and want_action
+        ann = np.ascontiguousarray(annotated_counts, dtype=np.float64)
+        mq = np.empty(t_end - t_begin, dtype=np.float64)
+        sc = np.empty((t_end - t_begin, O), dtype=np.float32) if want_scores else None
+        q = np.empty(T, dtype=np.float32) if full else None
+        nf = C.c_int(-1)
+        check(lib.ivosw_round_device(self._h, _ptr(all_F), _ptr(all_P), T, O, H, W, t_begin, t_end, _np_ptr(ann),
+                                     _np_ptr(mq), _np_ptr(sc), _np_ptr(q), C.byref(nf) if full else None,
+                                     _stream(self.device)))
+        return {"mask_quality": mq, "scores": sc, "q": q, "next_frame": int(nf.value) if full else None}
+
+    def round_host(self, all_F, all_P, annotated_counts, want_scores=False):
+        """Same round from host tensors (pinned or pageable CPU fp32, contiguous)."""
+        if all_F.device.type != "cpu" or all_P.device.type != "cpu":
+            raise ValueError("round_host takes CPU tensors")
+        all_F = all_F.contiguous().float()
+        all_P = all_P.contiguous().float()
+        T, _, H, W = all_F.shape
+        O = all_P.shape[1] - 1
+        ann = np.ascontiguousarray(annotated_counts, dtype=np.float64)
+        mq = np.empty(T, dtype=np.float64)
+        sc = np.empty((T, O), dtype=np.float32) if want_scores else None
+        q = np.empty(T, dtype=np.float32)
+        nf = C.c_int(-1)
+        check(lib.ivosw_round_host(self._h, _ptr(all_F), _ptr(all_P), T, O, H, W, _np_ptr(ann), _np_ptr(mq),
+                                   _np_ptr(sc), _np_ptr(q), C.byref(nf), _stream(self.device)))
+        return {"mask_quality": mq, "scores": sc, "q": q, "next_frame": int(nf.value)}
+
+    def agent_action(self, mask_quality, annotated_counts):
+        """Greedy Agent.action on host vectors (float64): returns (next_frame, q[T])."""
+        mqa = np.ascontiguousarray(mask_quality, dtype=np.float64)
+        ann = np.ascontiguousarray(annotated_counts, dtype=np.float64)
+        T = mqa.shape[0]
+        q = np.empty(T, dtype=np.float32)
+        nf = C.c_int(-1)
+        check(lib.ivosw_agent_action(self._h, _np_ptr(mqa), _np_ptr(ann), T, _np_ptr(q), C.byref(nf),
+                                     _stream(self.device)))
+        return int(nf.value), q
+
+    # ------------------------------------------------------------------ MANet tail (utils/utils_manet.py)
+    def manet_tail(self, logits, H, W, masks_out=None, all_p_out=None, want_masks=True, want_probs=True):
+        """logits: T x C x h x w CUDA fp32 -> (masks T x H x W fp32, all_P T x C x H x W fp32)."""
+        logits = self._dev32(logits)
+        T, Cn, h, w = logits.shape
+        if want_masks and masks_out is None:
+            masks_out = torch.empty((T, H, W), device=self.device, dtype=torch.float32)
+        if want_probs and all_p_out is None:
+            all_p_out = torch.empty((T, Cn, H, W), device=self.device, dtype=torch.float32)
+        check(lib.ivosw_manet_tail(self._h, _ptr(logits), T, Cn, h, w, H, W, _ptr(masks_out if want_masks else None),
+                                   _ptr(all_p_out if want_probs else None), _stream(self.device)))
+        return masks_out, all_p_out
+
+    # ------------------------------------------------------------------ helpers
+    def _dev32(self, t):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        if t.device != self.device or t.dtype != torch.float32:
+            t = t.to(self.device, torch.float32)
+        return t if t.is_contiguous() else t.contiguous()
+
+
+_ENGINES = {}
+
+
+def get_engine(device=None, conv_mode=None):
+    """Process-wide engine per CUDA device (what the drop-in modules share)."""
+    if device is None:
+        device = torch.cuda.current_device()
+    dev = torch.device(device if not isinstance(device, int) else "cuda:%d" % device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    e = _ENGINES.get(idx)
+    if e is None:
+        e = Engine(idx, conv_mode or DEFAULT_CONV_MODE)
+        _ENGINES[idx] = e
+    elif conv_mode is not None and conv_mode != e.conv_mode:
+        e.set_conv_mode(conv_mode)
+    return e

@@ -118,12 +118,16 @@ def grid_sample_bilinear(img, gx, gy):
     B, C, H, W = img.shape
     ix = ((gx + 1) / 2) * (W - 1)
     iy = ((gy + 1) / 2) * (H - 1)
+    # weights as ATen's vectorised CPU kernel forms them (GridSamplerKernel.cpp, bilinear):
+    # w = x - floor(x); e = 1 - w; n = y - floor(y); s = 1 - n; nw = s*e, ne = s*w, sw = n*e, se = n*w
     x0 = torch.floor(ix); y0 = torch.floor(iy)
     x1 = x0 + 1; y1 = y0 + 1
-    w_nw = (x1 - ix) * (y1 - iy)
-    w_ne = (ix - x0) * (y1 - iy)
-    w_sw = (x1 - ix) * (iy - y0)
-    w_se = (ix - x0) * (iy - y0)
+    w = ix - x0; e = 1 - w
+    n = iy - y0; s_ = 1 - n
+    w_nw = s_ * e
+    w_ne = s_ * w
+    w_sw = n * e
+    w_se = n * w
     flat = img.reshape(B, C, H * W)
     out = torch.zeros((B, C) + tuple(gx.shape[1:]), dtype=img.dtype)
 

@@ -1,0 +1,179 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the CPU oracle and the
+committed golden fixtures (generated from the reference's own modules).
+
+Tolerances (stated by north_star: argmax bit-exact, fp within tolerance):
+  boxes           bit-exact (integer / float64 arithmetic)
+  ROI crop        |d| <= 2e-6          (same rounding sequence as ATen's CPU kernels)
+  r2..r5 probes   |d| <= 1e-4 + 1e-4*|ref|
+  quality scores  |d| <= 1e-4
+  Q-values        |d| <= 1e-5
+  next_frame      identical (unless the fp64 arbiter's top-2 gap is below 1e-6, reported)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ivosw import synth
+
+pytestmark = pytest.mark.gpu
+
+CONV_MODE = os.environ.get("IVOSW_CONV_MODE", "simt_fp32")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ivosw.engine import Engine
+    e = Engine(0, CONV_MODE)
+    e.load_assess(synth.assess_state_dict(0))
+    e.load_brain(synth.brain_state_dict(0))
+    yield e
+    e.close()
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def test_brain_vs_golden_and_oracle(eng, golden_dir):
+    from oracle import brain_ref
+    g = _g(golden_dir, "brain")
+    for seed in (0, 1):
+        sd = synth.brain_state_dict(seed)
+        eng.load_brain(sd)
+        for (N, T) in ((1, 1), (1, 8), (1, 64), (1, 128), (4, 25)):
+            x = g["s%d_N%d_T%d_x" % (seed, N, T)]
+            q, am = eng.brain_forward(torch.from_numpy(x).float().cuda(), want_argmax=True)
+            q = q.cpu().numpy()
+            ref32 = g["s%d_N%d_T%d_f32_q" % (seed, N, T)]
+            ref64 = g["s%d_N%d_T%d_f64_q" % (seed, N, T)]
+            np.testing.assert_allclose(q, ref32, rtol=0, atol=1e-5)
+            np.testing.assert_allclose(q, ref64, rtol=0, atol=1e-5)
+            np.testing.assert_array_equal(am.cpu().numpy(), ref32.argmax(1))
+    # random states, longer clips, vs the oracle
+    sd = synth.brain_state_dict(0)
+    eng.load_brain(sd)
+    sdn = {k: v.numpy() for k, v in sd.items()}
+    rng = np.random.default_rng(3)
+    flips = 0
+    for trial in range(24):
+        T = int(rng.integers(2, 200))
+        x = np.stack([rng.uniform(0.2, 0.95, T), rng.integers(0, 3, T).astype(np.float64)], 1)[None]
+        q, am = eng.brain_forward(torch.from_numpy(x).float().cuda(), want_argmax=True)
+        ref = brain_ref.brain_forward(sdn, x, np.float32)
+        np.testing.assert_allclose(q.cpu().numpy(), ref, rtol=0, atol=1e-5)
+        flips += int(am.item() != ref[0].argmax())
+    assert flips == 0
+
+
+def test_boxes_bit_exact(eng, golden_dir):
+    g = _g(golden_dir, "boxes")
+    masks = np.unpackbits(g["masks"], axis=-1)[..., :854].astype(np.float32)
+    B, H, W = masks.shape
+    tf = torch.zeros((B, 3, H, W), device="cuda")
+    tp = torch.from_numpy(masks * 0.8 + 0.1).cuda()           # probabilities 0.9 / 0.1
+    _, boxes = eng.assess_forward(tf, tp, want_boxes=True)
+    np.testing.assert_array_equal(boxes.cpu().numpy(), g["boxes"])
+    small = g["small"]
+    _, boxes = eng.assess_forward(torch.zeros((3, 3, 37, 53), device="cuda"), torch.from_numpy(small * 0.9).cuda(),
+                                  want_boxes=True)
+    np.testing.assert_array_equal(boxes.cpu().numpy(), g["boxes_small"])
+    # threshold is strict: exactly 0.5 is background (tp > 0.5)
+    tp = torch.full((1, 200, 300), 0.5, device="cuda")
+    _, b = eng.assess_forward(torch.zeros((1, 3, 200, 300), device="cuda"), tp, want_boxes=True)
+    from oracle import assess_ref
+    np.testing.assert_array_equal(b.cpu().numpy(), assess_ref.all2yxhw(np.zeros((1, 200, 300), np.float32), 1.5))
+
+
+@pytest.mark.parametrize("name", ["round_c1", "round_atnet_small", "round_single", "round_t16"])
+def test_round_vs_golden(eng, golden_dir, name):
+    g = _g(golden_dir, name)
+    clip_id, T, H, W, O, seed = [int(v) for v in g["meta"]]
+    all_F, all_P, annotated = synth.make_clip(clip_id, T, H, W, O, str(g["style"]))
+    eng.load_assess(synth.assess_state_dict(seed))
+    eng.load_brain(synth.brain_state_dict(seed))
+    F_d, P_d = torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda()
+    eng.enable_probes(True)
+    for o in range(O):
+        s, boxes = eng.assess_forward(F_d, P_d[:, o + 1], want_boxes=True)
+        np.testing.assert_array_equal(boxes.cpu().numpy(), g["f32_boxes"][o])
+        crop = eng.probe(0).cpu().numpy()                        # T x 4 x 256 x 256, RGB normalised
+        mean = np.array([0.485, 0.456, 0.406], np.float32)[None, :, None, None]
+        std = np.array([0.229, 0.224, 0.225], np.float32)[None, :, None, None]
+        np.testing.assert_allclose(crop[:, :3, ::8, ::8] * std + mean, g["roi_f"][o], atol=2e-6)
+        np.testing.assert_allclose(crop[:, 3, ::8, ::8], g["roi_p"][o], atol=2e-6)
+        for which, (k, step) in enumerate((("pool", 8), ("r2", 8), ("r3", 4), ("r4", 2), ("r5", 1)), start=1):
+            t = eng.probe(which).cpu().numpy()
+            probe = t[:, ::max(1, t.shape[1] // 8), ::step, ::step]
+            np.testing.assert_allclose(probe, g[k][o], atol=1e-4, rtol=1e-4, err_msg=k)
+        np.testing.assert_allclose(s.cpu().numpy(), g["f32_scores"][:, o], atol=1e-4)
+    eng.enable_probes(False)
+    r = eng.round_device(F_d, P_d, synth.annotated_counts(annotated, T), want_scores=True)
+    np.testing.assert_allclose(r["scores"], g["f32_scores"], atol=1e-4)
+    np.testing.assert_allclose(r["mask_quality"], g["f32_mask_quality"], atol=1e-4)
+    np.testing.assert_allclose(r["q"], g["f32_q"], atol=1e-5)
+    q64 = np.sort(g["f64_q"])[::-1]
+    if T == 1 or q64[0] - q64[1] > 1e-6:
+        assert r["next_frame"] == int(g["f32_next_frame"])
+    # host-buffer entry point gives the same answer
+    rh = eng.round_host(torch.from_numpy(all_F), torch.from_numpy(all_P), synth.annotated_counts(annotated, T))
+    assert rh["next_frame"] == r["next_frame"]
+    np.testing.assert_array_equal(rh["mask_quality"], r["mask_quality"])
+
+
+def test_round_vs_oracle_480p(eng):
+    """One clip at the headline resolution (T kept small so the CPU oracle finishes in seconds)."""
+    from oracle import round_ref
+    T, H, W, O = 6, 480, 854, 2
+    all_F, all_P, annotated = synth.make_clip(11, T, H, W, O)
+    assess_sd, brain_sd = synth.assess_state_dict(0), synth.brain_state_dict(0)
+    eng.load_assess(assess_sd)
+    eng.load_brain(brain_sd)
+    r = eng.round_device(torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda(),
+                         synth.annotated_counts(annotated, T), want_scores=True)
+    ref = round_ref.recommend_frame_wild_ours(assess_sd, brain_sd, all_F, all_P, annotated)
+    np.testing.assert_allclose(r["scores"], ref["scores"], atol=1e-4)
+    np.testing.assert_allclose(r["q"], ref["q"], atol=1e-5)
+    assert r["next_frame"] == ref["next_frame"]
+
+
+def test_round_properties_full_size(eng):
+    """BASELINE config C2 size (T=64, 480p, O=2): size-independent properties instead of the oracle.
+    (1) sharding invariance: scoring frame ranges separately gives the same mask_quality bit for bit;
+    (2) chunking invariance; (3) determinism; (4) frame permutation permutes the scores."""
+    T, H, W, O = 64, 480, 854, 2
+    all_F, all_P, annotated = synth.make_clip(0, T, H, W, O)
+    eng.load_assess(synth.assess_state_dict(0))
+    eng.load_brain(synth.brain_state_dict(0))
+    F_d, P_d = torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda()
+    ann = synth.annotated_counts(annotated, T)
+    full = eng.round_device(F_d, P_d, ann, want_scores=True)
+    again = eng.round_device(F_d, P_d, ann, want_scores=True)
+    np.testing.assert_array_equal(full["scores"], again["scores"])
+    assert full["next_frame"] == again["next_frame"]
+    parts = [eng.round_device(F_d, P_d, ann, t_begin=a, t_end=b)["mask_quality"] for a, b in ((0, 8), (8, 40), (40, 64))]
+    np.testing.assert_array_equal(np.concatenate(parts), full["mask_quality"])
+    nf, q = eng.agent_action(full["mask_quality"], ann)
+    assert nf == full["next_frame"]
+    np.testing.assert_array_equal(q, full["q"])
+    perm = np.random.default_rng(0).permutation(T)
+    pr = eng.round_device(F_d[perm].contiguous(), P_d[perm].contiguous(), ann, want_scores=True)
+    np.testing.assert_array_equal(pr["scores"], full["scores"][perm])
+    assert np.isfinite(full["q"]).all() and 0 <= full["next_frame"] < T
+
+
+def test_manet_tail(eng, golden_dir):
+    g = _g(golden_dir, "manet_tail")
+    H, W = [int(v) for v in g["hw"]]
+    logits = torch.from_numpy(g["logits"]).cuda()
+    masks, all_P = eng.manet_tail(logits, H, W)
+    np.testing.assert_allclose(all_P.cpu().numpy(), g["all_P"], atol=2e-6)
+    # masks: identical except where the top-2 upsampled logits tie to fp32 rounding
+    up = torch.nn.functional.interpolate(torch.from_numpy(g["logits"]).double(), size=(H, W), mode="bilinear",
+                                         align_corners=True)
+    top2 = up.topk(2, dim=1).values
+    near_tie = ((top2[:, 0] - top2[:, 1]) < 1e-6).numpy()
+    diff = masks.cpu().numpy().astype(np.uint8) != g["masks"]
+    assert not (diff & ~near_tie).any()
+    assert diff.sum() <= near_tie.sum()
