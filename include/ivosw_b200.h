@@ -146,6 +146,29 @@ IVOSW_API int ivosw_agent_action(ivosw_ctx* ctx, const double* mask_quality_host
                        const double* annotated_counts_host, int T,
                        float* q_host, int* next_frame, void* stream);
 
+/* ---- frame-sharded round (multi-GPU) -----------------------------------
+ * ivosw_score_shard: the scoring half of the round for frames [t_begin, t_end), fully
+ * asynchronous: writes the float64 per-frame mean quality to mq_dev (device, t_end - t_begin
+ * doubles — e.g. this rank's slice of the all-gather buffer) and, if scores_dev is not NULL,
+ * the per-object scores as [O][t_end - t_begin] fp32.  No host synchronisation.
+ * ivosw_agent_action_dev: Brain + argmax on the gathered device vector mq_dev[T]
+ * (annotated_counts_host: T doubles); synchronises the stream and returns q / index on the host. */
+IVOSW_API int ivosw_score_shard(ivosw_ctx* ctx, const float* frames_dev, const float* probs_dev,
+                      int T, int O, int H, int W, int t_begin, int t_end,
+                      double* mq_dev, float* scores_dev, void* stream);
+IVOSW_API int ivosw_agent_action_dev(ivosw_ctx* ctx, const double* mq_dev, const double* annotated_counts_host,
+                           int T, float* q_host, int* next_frame, void* stream);
+
+/* ---- per-stage device timing (bench.py's roofline leg) ----------------------------------------
+ * While enabled, CUDA events are recorded on the launching stream around each stage of every
+ * chunk; ivosw_stage_times synchronises them and returns the accumulated milliseconds since the
+ * last reset: [0] bbox+ROI crop, [1] stem conv+maxpool, [2] res2..res5 conv stack, [3] pool+FC,
+ * [4] Brain (3 launches), and the number of conv-stack launches in n_conv_launches. */
+#define IVOSW_NUM_STAGES 5
+IVOSW_API int ivosw_stage_timing(ivosw_ctx* ctx, int enable);
+IVOSW_API int ivosw_stage_times(ivosw_ctx* ctx, float* ms_out /*[IVOSW_NUM_STAGES]*/, long long* n_conv_launches,
+                      int reset);
+
 /* ---- MANet round tail (utils/utils_manet.py:76-81,109-114,146-150,160-161) ---------------
  * logits_dev: T x C x h x w fp32 (C = O+1).  Bilinear upsample (align_corners=True) to
  * H x W, per-pixel first-max argmax -> masks_dev (T x H x W fp32, nullable), channel

@@ -40,6 +40,36 @@ void release(DeviceBuffer& b) {
     b.p = nullptr; b.bytes = 0;
 }
 
+static cudaEvent_t take_event(ivosw_ctx* c) {
+    cudaEvent_t e = nullptr;
+    if (!c->evt_pool.empty()) { e = c->evt_pool.back(); c->evt_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+
+int stage_begin(ivosw_ctx* c, int stage, cudaStream_t s) {
+    if (!c->timing_on) return -1;
+    ivosw_ctx::StageEvt ev{stage, take_event(c), take_event(c)};
+    cudaEventRecord(ev.a, s);
+    c->stage_evts.push_back(ev);
+    return (int)c->stage_evts.size() - 1;
+}
+
+void stage_end(ivosw_ctx* c, int idx, cudaStream_t s) {
+    if (idx >= 0) cudaEventRecord(c->stage_evts[idx].b, s);
+}
+
+static void drain_stage_events(ivosw_ctx* c) {
+    for (auto& ev : c->stage_evts) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.b) == cudaSuccess && cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess)
+            c->stage_ms[ev.stage] += ms;
+        c->evt_pool.push_back(ev.a);
+        c->evt_pool.push_back(ev.b);
+    }
+    c->stage_evts.clear();
+}
+
 std::vector<ConvLayer> make_resnet50_layers() {
     // mirrors ivosw/arch.py::resnet50_convs — torchvision Bottleneck, stride on the 3x3 conv
     std::vector<ConvLayer> v;
@@ -135,12 +165,18 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
     for (int done = 0; done < n_units; done += cap) {
         const int B = std::min(cap, n_units - done);
         ua.u0 = u_first + done;
+        int tk = stage_begin(c, 0, s);
         if ((rc = launch_bbox(c, ua, B, H, W, s))) return rc;
         if ((rc = launch_roi_sample(c, ua, B, H, W, boxes_dev ? boxes_dev + 4 * (size_t)done : (float*)c->boxes.p, s)))
             return rc;
+        stage_end(c, tk, s);
         if ((rc = keep_probe(c, 0, (const float*)c->crop.p, (size_t)B * ROI * ROI * 4, s))) return rc;
+        tk = stage_begin(c, 1, s);
         if ((rc = launch_stem(c, B, s))) return rc;
+        stage_end(c, tk, s);
         if ((rc = keep_probe(c, 1, (const float*)c->pool.p, (size_t)B * 64 * 64 * 64, s))) return rc;
+        tk = stage_begin(c, 2, s);
+        const long long launches_before = c->launches;
         const float* x = (const float*)c->pool.p;
         float* outs[2] = {(float*)c->actX.p, (float*)c->actY.p};
         int flip = 0, stage_probe = 2;
@@ -167,7 +203,11 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
                 }
             }
         }
+        stage_end(c, tk, s);
+        if (tk >= 0) c->conv_launches_timed += c->launches - launches_before;
+        tk = stage_begin(c, 3, s);
         if ((rc = launch_gap_fc(c, x, B, score_dev + done, s))) return rc;
+        stage_end(c, tk, s);
         c->last_chunk_b = B;
     }
     return IVOSW_OK;
@@ -236,6 +276,8 @@ void ivosw_destroy(ivosw_ctx* c) {
                             &c->actT1, &c->actT2, &c->scores, &c->mq, &c->stage_frames, &c->stage_probs};
     for (DeviceBuffer* b : bufs) release(*b);
     for (DeviceBuffer& b : c->probe_buf) release(b);
+    drain_stage_events(c);
+    for (cudaEvent_t e : c->evt_pool) cudaEventDestroy(e);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
@@ -358,13 +400,40 @@ int ivosw_assess_probe(ivosw_ctx* c, int which, float* out_dev, size_t capacity_
 }
 
 // ------------------------------------------------------------------------------------------- round
-static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
-                      int t_begin, int t_end, const double* ann_host, double* mq_host, float* scores_host,
-                      float* q_host, int* next_frame, cudaStream_t s) {
+// scoring half of a round for frames [t_begin, t_end): asynchronous, device outputs only
+static int score_shard(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
+                       int t_begin, int t_end, const double* ann_dev, double* mq_dev, float* state_dev,
+                       float* scores_dev_out, cudaStream_t s) {
     const int Tl = t_end - t_begin;
     const long long HW = (long long)H * W;
     int rc;
     if ((rc = ensure(c->scores, sizeof(float) * (size_t)Tl * O))) return rc;
+    UnitAddr ua{frames_dev + (long long)t_begin * 3 * HW, 3 * HW,
+                probs_dev + ((long long)t_begin * (O + 1) + 1) * HW, (long long)(O + 1) * HW, HW, Tl, 0};
+    if ((rc = assess_units(c, ua, Tl * O, H, W, (float*)c->scores.p, nullptr, s))) return rc;
+    int tk = stage_begin(c, 3, s);
+    if ((rc = launch_object_mean(c, (const float*)c->scores.p, Tl, O, ann_dev ? ann_dev + t_begin : nullptr, mq_dev,
+                                 ann_dev ? state_dev : nullptr, s)))
+        return rc;
+    stage_end(c, tk, s);
+    if (scores_dev_out)
+        IVOSW_CUDA(cudaMemcpyAsync(scores_dev_out, c->scores.p, sizeof(float) * (size_t)Tl * O,
+                                   cudaMemcpyDeviceToDevice, s));
+    return IVOSW_OK;
+}
+
+static int timed_brain(ivosw_ctx* c, int T, cudaStream_t s) {
+    int tk = stage_begin(c, 4, s);
+    int rc = launch_brain(c, (const float*)c->brain_state.p, 1, T, (float*)c->brain_q.p, (int*)c->brain_arg.p, s);
+    stage_end(c, tk, s);
+    return rc;
+}
+
+static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
+                      int t_begin, int t_end, const double* ann_host, double* mq_host, float* scores_host,
+                      float* q_host, int* next_frame, cudaStream_t s) {
+    const int Tl = t_end - t_begin;
+    int rc;
     // mq buffer: [Tl doubles mq][T doubles ann]
     if ((rc = ensure(c->mq, sizeof(double) * ((size_t)Tl + T)))) return rc;
     if ((rc = ensure(c->brain_state, sizeof(float) * 2 * (size_t)T))) return rc;
@@ -380,20 +449,15 @@ static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_
 
     double* mq_dev = (double*)c->mq.p;
     double* ann_dev = mq_dev + Tl;
-    const bool full = (t_begin == 0 && t_end == T);
+    const bool full = (t_begin == 0 && t_end == T) && (q_host || next_frame);
+    if (full && !c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
     memcpy(pin_ann, ann_host, sizeof(double) * T);
     IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, s));
-
-    UnitAddr ua{frames_dev + (long long)t_begin * 3 * HW, 3 * HW,
-                probs_dev + ((long long)t_begin * (O + 1) + 1) * HW, (long long)(O + 1) * HW, HW, Tl, 0};
-    if ((rc = assess_units(c, ua, Tl * O, H, W, (float*)c->scores.p, nullptr, s))) return rc;
-    if ((rc = launch_object_mean(c, (const float*)c->scores.p, Tl, O, ann_dev + t_begin, mq_dev,
-                                 full ? (float*)c->brain_state.p : nullptr, s)))
+    if ((rc = score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, ann_dev, mq_dev,
+                          full ? (float*)c->brain_state.p : nullptr, nullptr, s)))
         return rc;
-    if (full && (q_host || next_frame)) {
-        if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
-        if ((rc = launch_brain(c, (const float*)c->brain_state.p, 1, T, (float*)c->brain_q.p, (int*)c->brain_arg.p, s)))
-            return rc;
+    if (full) {
+        if ((rc = timed_brain(c, T, s))) return rc;
         IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
         IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     }
@@ -467,6 +531,64 @@ int ivosw_agent_action(ivosw_ctx* c, const double* mq_host, const double* ann_ho
     IVOSW_CUDA(cudaStreamSynchronize(s));
     if (q_host) memcpy(q_host, pin_q, sizeof(float) * T);
     if (next_frame) *next_frame = *pin_arg;
+    return IVOSW_OK;
+}
+
+int ivosw_score_shard(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
+                      int t_begin, int t_end, double* mq_dev, float* scores_dev, void* stream) {
+    IVOSW_REQUIRE(c && frames_dev && probs_dev && mq_dev, "null pointer");
+    IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 2 && W >= 2, "T, O, H, W");
+    IVOSW_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= T, "frame range");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, nullptr, mq_dev, nullptr, scores_dev,
+                       (cudaStream_t)stream);
+}
+
+int ivosw_agent_action_dev(ivosw_ctx* c, const double* mq_dev, const double* ann_host, int T, float* q_host,
+                           int* next_frame, void* stream) {
+    IVOSW_REQUIRE(c && mq_dev && ann_host, "null pointer");
+    IVOSW_REQUIRE(T >= 1, "T");
+    if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure(c->mq, sizeof(double) * 2 * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_state, sizeof(float) * 2 * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_q, sizeof(float) * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_arg, sizeof(int)))) return rc;
+    if ((rc = ensure_pinned(c, sizeof(double) * T + sizeof(float) * T + 64))) return rc;
+    double* pin_ann = (double*)c->pinned_small;
+    float* pin_q = (float*)(pin_ann + T);
+    int* pin_arg = (int*)(pin_q + T);
+    double* ann_dev = (double*)c->mq.p + T;   // second half of the mq buffer (first half may be mq_dev itself)
+    memcpy(pin_ann, ann_host, sizeof(double) * T);
+    IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_pack_state(c, mq_dev, ann_dev, T, (float*)c->brain_state.p, s))) return rc;
+    if ((rc = timed_brain(c, T, s))) return rc;
+    IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
+    IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IVOSW_CUDA(cudaStreamSynchronize(s));
+    if (q_host) memcpy(q_host, pin_q, sizeof(float) * T);
+    if (next_frame) *next_frame = *pin_arg;
+    return IVOSW_OK;
+}
+
+int ivosw_stage_timing(ivosw_ctx* c, int enable) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    c->timing_on = enable != 0;
+    return IVOSW_OK;
+}
+
+int ivosw_stage_times(ivosw_ctx* c, float* ms_out, long long* n_conv_launches, int reset) {
+    IVOSW_REQUIRE(c && ms_out, "null pointer");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    drain_stage_events(c);
+    for (int i = 0; i < IVOSW_NUM_STAGES; ++i) ms_out[i] = c->stage_ms[i];
+    if (n_conv_launches) *n_conv_launches = c->conv_launches_timed;
+    if (reset) {
+        for (int i = 0; i < IVOSW_NUM_STAGES; ++i) c->stage_ms[i] = 0.f;
+        c->conv_launches_timed = 0;
+    }
     return IVOSW_OK;
 }
 

@@ -55,6 +55,22 @@ __global__ void object_mean_kernel(const float* __restrict__ scores, int T, int 
     }
 }
 
+__global__ void pack_state_kernel(const double* __restrict__ mq, const double* __restrict__ ann, int T,
+                                  float* __restrict__ state) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    state[2 * t + 0] = (float)mq[t];   // torch.Tensor(state[None]): float64 -> float32 (agent.py:176)
+    state[2 * t + 1] = (float)ann[t];
+}
+
+int launch_pack_state(ivosw_ctx* c, const double* mq_dev, const double* ann_dev, int T, float* state_dev,
+                      cudaStream_t s) {
+    pack_state_kernel<<<(T + 127) / 128, 128, 0, s>>>(mq_dev, ann_dev, T, state_dev);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
 int launch_object_mean(ivosw_ctx* c, const float* scores, int T, int O, const double* ann_dev, double* mq_dev,
                        float* state_dev, cudaStream_t s) {
     object_mean_kernel<<<(T + 127) / 128, 128, 0, s>>>(scores, T, O, ann_dev, mq_dev, state_dev);

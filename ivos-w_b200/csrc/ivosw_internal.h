@@ -103,6 +103,14 @@ struct ivosw_ctx {
     int last_chunk_b = 0;
     ivosw::DeviceBuffer probe_buf[6];   // fp32 NHWC copies: crop, pool, r2, r3, r4, r5
 
+    // per-stage timing (ivosw_stage_timing)
+    bool timing_on = false;
+    struct StageEvt { int stage; cudaEvent_t a, b; };
+    std::vector<StageEvt> stage_evts;
+    std::vector<cudaEvent_t> evt_pool;
+    float stage_ms[IVOSW_NUM_STAGES] = {0, 0, 0, 0, 0};
+    long long conv_launches_timed = 0;
+
     // host-staged rounds
     ivosw::DeviceBuffer stage_frames, stage_probs;
     void* pinned_small = nullptr;    // small pinned scratch for D2H results
@@ -115,6 +123,9 @@ struct ivosw_ctx {
 namespace ivosw {
 
 int ensure(DeviceBuffer& b, size_t bytes);
+// RAII-free stage bracket: stage_begin returns an index (or -1 when timing is off)
+int stage_begin(ivosw_ctx* c, int stage, cudaStream_t s);
+void stage_end(ivosw_ctx* c, int idx, cudaStream_t s);
 void release(DeviceBuffer& b);
 
 // ---- roi.cu
@@ -129,6 +140,8 @@ int launch_conv_simt(ivosw_ctx* c, const ConvLayer& L, const float* in, const fl
 int launch_gap_fc(ivosw_ctx* c, const float* r5, int B, float* scores, cudaStream_t s);
 int launch_object_mean(ivosw_ctx* c, const float* scores, int T, int O, const double* ann_dev, double* mq_dev,
                        float* state_dev, cudaStream_t s);
+int launch_pack_state(ivosw_ctx* c, const double* mq_dev, const double* ann_dev, int T, float* state_dev,
+                      cudaStream_t s);
 // ---- brain.cu
 int brain_pack(ivosw_ctx* c);
 int launch_brain(ivosw_ctx* c, const float* state, int N, int T, float* q, int* argmax, cudaStream_t s);

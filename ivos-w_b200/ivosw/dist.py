@@ -1,0 +1,60 @@
+"""Frame-sharded scoring round over the GPUs of one box.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink; gloo on CPU for the
+host-logic tests).  Rank r owns the contiguous frame range ``shard_range(T, G, r)``
+and scores it for every object; ONE all-gather of the per-frame float64 mean
+quality follows — the Q-network is a bidirectional LSTM over all frames, so the
+gather must precede it — and every rank then runs Brain + argmax redundantly on
+the identical vector (deterministic kernel -> identical index on every rank).
+No other collective is on the path.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(T, world, rank):
+    """Contiguous frame range of ``rank``: ceil(T / world) frames each, last shards may be short/empty."""
+    per = -(-T // world)
+    a = min(T, rank * per)
+    return a, min(T, a + per)
+
+
+def gather_layout(T, world):
+    """(per, padded_T): the all-gather moves ``per`` doubles per rank."""
+    per = -(-T // world)
+    return per, per * world
+
+
+def sharded_round(engine, all_F, all_P, annotated_counts, group=None):
+    """all_F / all_P: this rank's FULL-clip tensors are not needed — only rows [a, b) are read, so callers
+    may pass tensors whose other rows are uninitialised.  Returns (next_frame, q[T], mask_quality[T])."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    T = all_F.shape[0]
+    per, padded = gather_layout(T, world)
+    a, b = shard_range(T, world, rank)
+    buf = torch.zeros(padded, dtype=torch.float64, device=engine.device)
+    if b > a:
+        engine.score_shard(all_F, all_P, a, b, buf[rank * per: rank * per + (b - a)])
+    if world > 1:
+        dist.all_gather_into_tensor(buf, buf[rank * per:(rank + 1) * per].clone(), group=group)
+    nf, q = engine.agent_action_dev(buf[:T], annotated_counts)
+    return nf, q, buf[:T]
+
+
+def host_gather_round(local_mq, T, annotated_counts, action_fn, group=None):
+    """Backend-agnostic form of the same protocol on host vectors (used by the gloo CPU tests of
+    the sharding logic): local_mq is this rank's float64 slice."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per, padded = gather_layout(T, world)
+    send = torch.zeros(per, dtype=torch.float64)
+    send[: len(local_mq)] = torch.as_tensor(np.asarray(local_mq), dtype=torch.float64)
+    out = torch.zeros(padded, dtype=torch.float64)
+    if world > 1:
+        dist.all_gather_into_tensor(out, send, group=group)
+    else:
+        out[:per] = send
+    mq = out[:T].numpy()
+    return action_fn(mq, annotated_counts), mq

@@ -206,6 +206,38 @@ class Engine:
                                      _stream(self.device)))
         return int(nf.value), q
 
+    # ------------------------------------------------------------------ frame-sharded round
+    def score_shard(self, all_F, all_P, t_begin, t_end, mq_out, scores_out=None):
+        """Asynchronous scoring of frames [t_begin, t_end): writes float64 per-frame quality into the
+        CUDA tensor ``mq_out`` (length t_end - t_begin; typically a slice of the all-gather buffer)."""
+        T, _, H, W = all_F.shape
+        O = all_P.shape[1] - 1
+        assert mq_out.dtype == torch.float64 and mq_out.is_cuda and mq_out.is_contiguous()
+        assert mq_out.numel() == t_end - t_begin
+        check(lib.ivosw_score_shard(self._h, _ptr(all_F), _ptr(all_P), T, O, H, W, t_begin, t_end, _ptr(mq_out),
+                                    _ptr(scores_out), _stream(self.device)))
+
+    def agent_action_dev(self, mq_dev, annotated_counts):
+        """Brain + argmax on a device float64 quality vector (after the all-gather)."""
+        T = mq_dev.numel()
+        ann = np.ascontiguousarray(annotated_counts, dtype=np.float64)
+        q = np.empty(T, dtype=np.float32)
+        nf = C.c_int(-1)
+        check(lib.ivosw_agent_action_dev(self._h, _ptr(mq_dev), _np_ptr(ann), T, _np_ptr(q), C.byref(nf),
+                                         _stream(self.device)))
+        return int(nf.value), q
+
+    def stage_timing(self, on=True):
+        check(lib.ivosw_stage_timing(self._h, 1 if on else 0))
+
+    def stage_times(self, reset=True):
+        """Accumulated device milliseconds per stage since the last reset + number of conv launches."""
+        ms = (C.c_float * 5)()
+        n = C.c_longlong(0)
+        check(lib.ivosw_stage_times(self._h, ms, C.byref(n), 1 if reset else 0))
+        names = ("roi", "stem", "conv_stack", "head", "brain")
+        return dict(zip(names, [float(v) for v in ms])), int(n.value)
+
     # ------------------------------------------------------------------ MANet tail (utils/utils_manet.py)
     def manet_tail(self, logits, H, W, masks_out=None, all_p_out=None, want_masks=True, want_probs=True):
         """logits: T x C x h x w CUDA fp32 -> (masks T x H x W fp32, all_P T x C x H x W fp32)."""
