@@ -169,6 +169,15 @@ IVOSW_API int ivosw_stage_timing(ivosw_ctx* ctx, int enable);
 IVOSW_API int ivosw_stage_times(ivosw_ctx* ctx, float* ms_out /*[IVOSW_NUM_STAGES]*/, long long* n_conv_launches,
                       int reset);
 
+/* ---- test hook: one bottleneck convolution in isolation -------------------------------------
+ * Runs layer `layer_index` (0..51, execution order of res2..res5) on in_dev (B x H x W x Cin fp32
+ * NHWC) with optional residual_dev (B x OH x OW x Cout fp32 NHWC) into out_dev (fp32 NHWC), with
+ * its folded BatchNorm and ReLU, using `conv_mode`.  The tensor-core modes convert to and from the
+ * split-fp16 planes internally.  Lets tests compare the tcgen05 kernel with the fp32 CUDA-core
+ * kernel layer by layer.  dims_out (nullable) receives {cin, in_hw, cout, out_hw, k, stride}. */
+IVOSW_API int ivosw_debug_conv(ivosw_ctx* ctx, int layer_index, int conv_mode, const float* in_dev,
+                     const float* residual_dev, float* out_dev, int B, int* dims_out, void* stream);
+
 /* ---- MANet round tail (utils/utils_manet.py:76-81,109-114,146-150,160-161) ---------------
  * logits_dev: T x C x h x w fp32 (C = O+1).  Bilinear upsample (align_corners=True) to
  * H x W, per-pixel first-max argmax -> masks_dev (T x H x W fp32, nullable), channel

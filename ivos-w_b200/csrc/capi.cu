@@ -177,31 +177,72 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
         if ((rc = keep_probe(c, 1, (const float*)c->pool.p, (size_t)B * 64 * 64 * 64, s))) return rc;
         tk = stage_begin(c, 2, s);
         const long long launches_before = c->launches;
-        const float* x = (const float*)c->pool.p;
-        float* outs[2] = {(float*)c->actX.p, (float*)c->actY.p};
-        int flip = 0, stage_probe = 2;
-        for (size_t li = 0; li < c->layers.size(); ++li) {
-            const ConvLayer& L = c->layers[li];
-            if (L.first_of_block) {
-                if ((rc = launch_conv_simt(c, L, x, nullptr, (float*)c->actT1.p, B, s))) return rc;
-            } else if (L.k == 3) {
-                if ((rc = launch_conv_simt(c, L, (const float*)c->actT1.p, nullptr, (float*)c->actT2.p, B, s))) return rc;
-            } else if (L.is_downsample) {
-                if ((rc = launch_conv_simt(c, L, x, nullptr, (float*)c->actDS.p, B, s))) return rc;
-            } else {  // conv3 + residual + relu -> block output
-                const float* res = L.residual == 2 ? (const float*)c->actDS.p : x;
-                float* y = outs[flip];
-                if ((rc = launch_conv_simt(c, L, (const float*)c->actT2.p, res, y, B, s))) return rc;
-                x = y;
-                flip ^= 1;
-                // a stage ends where the next bottleneck opens with a downsample branch
-                const bool stage_end = (li + 1 == c->layers.size()) ||
-                                       (li + 3 < c->layers.size() && c->layers[li + 3].is_downsample);
-                if (stage_end) {
-                    if ((rc = keep_probe(c, stage_probe, x, (size_t)B * L.out_hw * L.out_hw * L.cout, s))) return rc;
-                    ++stage_probe;
+        const float* x = nullptr;      // fp32 NHWC r5 handed to the pooling/FC kernel
+        if (c->conv_mode == IVOSW_CONV_SIMT_FP32) {
+            x = (const float*)c->pool.p;
+            float* outs[2] = {(float*)c->actX.p, (float*)c->actY.p};
+            int flip = 0, stage_probe = 2;
+            for (size_t li = 0; li < c->layers.size(); ++li) {
+                const ConvLayer& L = c->layers[li];
+                if (L.first_of_block) {
+                    if ((rc = launch_conv_simt(c, L, x, nullptr, (float*)c->actT1.p, B, s))) return rc;
+                } else if (L.k == 3) {
+                    if ((rc = launch_conv_simt(c, L, (const float*)c->actT1.p, nullptr, (float*)c->actT2.p, B, s))) return rc;
+                } else if (L.is_downsample) {
+                    if ((rc = launch_conv_simt(c, L, x, nullptr, (float*)c->actDS.p, B, s))) return rc;
+                } else {  // conv3 + residual + relu -> block output
+                    const float* res = L.residual == 2 ? (const float*)c->actDS.p : x;
+                    float* y = outs[flip];
+                    if ((rc = launch_conv_simt(c, L, (const float*)c->actT2.p, res, y, B, s))) return rc;
+                    x = y;
+                    flip ^= 1;
+                    // a stage ends where the next bottleneck opens with a downsample branch
+                    const bool stage_end_ = (li + 1 == c->layers.size()) ||
+                                            (li + 3 < c->layers.size() && c->layers[li + 3].is_downsample);
+                    if (stage_end_) {
+                        if ((rc = keep_probe(c, stage_probe, x, (size_t)B * L.out_hw * L.out_hw * L.cout, s))) return rc;
+                        ++stage_probe;
+                    }
                 }
             }
+        } else {
+            // tensor-core path: activations live as split-fp16 planes inside the same workspace buffers
+            const int terms = c->conv_mode == IVOSW_CONV_TC_FP16X3 ? 3 : 1;
+            const SplitAct t1 = split_view(c->actT1), t2 = split_view(c->actT2), ds = split_view(c->actDS);
+            const SplitAct outs[2] = {split_view(c->actX), split_view(c->actY)};
+            SplitAct xs = split_view(c->c1);     // c1 is free once the max-pool has run
+            if ((rc = launch_split(c, (const float*)c->pool.p, xs, (long long)B * 64 * 64 * 64, s))) return rc;
+            int flip = 0, stage_probe = 2;
+            for (size_t li = 0; li < c->layers.size(); ++li) {
+                const ConvLayer& L = c->layers[li];
+                if (L.first_of_block) {
+                    if ((rc = launch_conv_tc(c, L, xs, nullptr, t1, B, terms, s))) return rc;
+                } else if (L.k == 3) {
+                    if ((rc = launch_conv_tc(c, L, t1, nullptr, t2, B, terms, s))) return rc;
+                } else if (L.is_downsample) {
+                    if ((rc = launch_conv_tc(c, L, xs, nullptr, ds, B, terms, s))) return rc;
+                } else {
+                    const SplitAct* res = L.residual == 2 ? &ds : &xs;
+                    const SplitAct y = outs[flip];
+                    if ((rc = launch_conv_tc(c, L, t2, res, y, B, terms, s))) return rc;
+                    xs = y;
+                    flip ^= 1;
+                    const bool stage_end_ = (li + 1 == c->layers.size()) ||
+                                            (li + 3 < c->layers.size() && c->layers[li + 3].is_downsample);
+                    if (stage_end_) {
+                        if (c->probes_on) {
+                            const size_t n = (size_t)B * L.out_hw * L.out_hw * L.cout;
+                            if ((rc = ensure(c->probe_buf[stage_probe], n * sizeof(float)))) return rc;
+                            if ((rc = launch_merge(c, xs, (float*)c->probe_buf[stage_probe].p, (long long)n, terms == 3, s)))
+                                return rc;
+                        }
+                        ++stage_probe;
+                    }
+                }
+            }
+            // r5 back to fp32 for the pooling/FC kernel (B x 64 x 2048: small)
+            if ((rc = launch_merge(c, xs, (float*)c->pool.p, (long long)B * 64 * 2048, terms == 3, s))) return rc;
+            x = (const float*)c->pool.p;
         }
         stage_end(c, tk, s);
         if (tk >= 0) c->conv_launches_timed += c->launches - launches_before;
@@ -590,6 +631,35 @@ int ivosw_stage_times(ivosw_ctx* c, float* ms_out, long long* n_conv_launches, i
         c->conv_launches_timed = 0;
     }
     return IVOSW_OK;
+}
+
+int ivosw_debug_conv(ivosw_ctx* c, int li, int conv_mode, const float* in_dev, const float* residual_dev,
+                     float* out_dev, int B, int* dims_out, void* stream) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    IVOSW_REQUIRE(li >= 0 && li < (int)c->layers.size(), "layer_index");
+    IVOSW_REQUIRE(conv_mode >= 0 && conv_mode <= 2, "conv_mode");
+    const ConvLayer& L = c->layers[li];
+    if (dims_out) {
+        dims_out[0] = L.cin; dims_out[1] = L.in_hw; dims_out[2] = L.cout; dims_out[3] = L.out_hw;
+        dims_out[4] = L.k; dims_out[5] = L.stride;
+    }
+    if (!in_dev) return IVOSW_OK;   // query only
+    IVOSW_REQUIRE(out_dev && B >= 1, "out_dev, B");
+    if (!c->assess_loaded) { set_error("AssessNet weights not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (conv_mode == IVOSW_CONV_SIMT_FP32) return launch_conv_simt(c, L, in_dev, residual_dev, out_dev, B, s);
+    int rc;
+    const size_t n_in = (size_t)B * L.in_hw * L.in_hw * L.cin, n_out = (size_t)B * L.out_hw * L.out_hw * L.cout;
+    if ((rc = ensure(c->actX, n_in * 4))) return rc;
+    if ((rc = ensure(c->actY, n_out * 4))) return rc;
+    if ((rc = ensure(c->actDS, n_out * 4))) return rc;
+    const SplitAct xin = split_view(c->actX), yout = split_view(c->actY), res = split_view(c->actDS);
+    const int terms = conv_mode == IVOSW_CONV_TC_FP16X3 ? 3 : 1;
+    if ((rc = launch_split(c, in_dev, xin, (long long)n_in, s))) return rc;
+    if (residual_dev && (rc = launch_split(c, residual_dev, res, (long long)n_out, s))) return rc;
+    if ((rc = launch_conv_tc(c, L, xin, residual_dev ? &res : nullptr, yout, B, terms, s))) return rc;
+    return launch_merge(c, yout, out_dev, (long long)n_out, terms == 3, s);
 }
 
 // -------------------------------------------------------------------------------------- MANet tail

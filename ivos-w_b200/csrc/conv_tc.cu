@@ -1,0 +1,509 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::f16, fp32 accumulation in
+// TMEM) fed by TMA, with the eval-mode BatchNorm scale/shift, residual add and ReLU fused in the
+// epilogue.  Serves every bottleneck convolution of res2..res5 (1x1, 3x3, stride 1 and 2).
+//
+//   out[m, n] = act( (sum_k A[m, k] W[n, k]) * scale[n] + shift[n] + residual[m, n] )
+//
+// fp32-grade arithmetic on fp16 tensor cores ("split-fp16", IVOSW_CONV_TC_FP16X3)
+//   every fp32 value x is stored as two fp16 planes  hi = fp16(x),  lo = fp16((x - hi) * 2048)
+//   so x = hi + lo/2048 to ~2^-22 relative, and a product is evaluated as three MMA terms
+//       D0 += A_hi W_hi                D1 += A_hi W_lo + A_lo W_hi            D = D0 + D1 / 2048
+//   (the lo*lo term, 2^-22 relative, is dropped).  Activations are WRITTEN in this split form by the
+//   epilogue, so the two planes cost exactly the bytes of one fp32 tensor.  IVOSW_CONV_TC_FP16X1
+//   issues only the first term (plain fp16 inputs).
+//
+// Implicit GEMM without im2col: activations are NHWC; a tile of 128 output pixels is always a set
+// of whole image rows (64x64: 2 rows, 32x32: 4, 16x16: 8, 8x8: two images), so for filter tap
+// (kh, kw) the A tile is ONE 5-d TMA box over the activation tensor, shifted by the tap offset, with
+// the hardware zero-filling the halo (padding).  Stride-2 convolutions use a 5-d view that splits
+// H and W into (half, parity) so that the same box shape applies.  K is walked as (tap, 64-channel
+// block); each step lands A_hi/A_lo (128 x 64 fp16, 128B-swizzled, K-major) and W_hi/W_lo
+// (BN x 64) in one pipeline stage.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 =
+// epilogue (two warps per TMEM lane quarter, each taking half of the tile's columns).  Persistent
+// CTAs walk the (m-tile, n-tile) list; TMEM holds two accumulator stages so the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "ivosw_internal.h"
+
+namespace ivosw {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;           // fp16 elements per K block = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 8;
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: no legitimate wait is this long
+
+struct TcTap { int c_add, w_add, p, h_add; };
+
+struct TcParams {
+    int M, Cout, Cin;
+    int num_taps, cin_blocks;     // K blocks = num_taps * cin_blocks
+    int out_hw;                   // OH == OW
+    int tiles_m, tiles_n;
+    int relu, terms;              // terms: 3 (split-fp16) or 1
+    const float* scale;
+    const float* shift;
+    const __half* res_hi;
+    const __half* res_lo;
+    __half* out_hi;
+    __half* out_lo;
+    TcTap taps[9];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((it & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > WAIT_TIMEOUT_CYCLES) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], M = 128, kind::f16, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on `bar` when all previously issued MMAs of this thread have completed (implies fence::before)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row atoms of 1024 bytes)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address        bits [0,14)
+    d |= (uint64_t)1 << 16;                               // leading byte offset  (ignored for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset   bits [32,46): 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                               // descriptor version   (sm_100)
+    d |= (uint64_t)2 << 61;                               // layout type          SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct TcSmem {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (BN == 64) ? 4 : 3;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ TcParams P) {
+    using S = TcSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]
+    uint64_t* empty_bar = bars + S::STAGES;          // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * S::STAGES;      // [2]
+    uint64_t* tempty_bar = bars + 2 * S::STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = P.tiles_m * P.tiles_n;
+    const int num_kb = P.num_taps * P.cin_blocks;
+    const bool x3 = P.terms == 3;
+    constexpr uint32_t TMEM_COLS = 4 * BN;           // 2 accumulator stages x (D0, D1)
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx_bytes = x3 ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
+            const int pix_per_img = P.out_hw * P.out_hw;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile % P.tiles_m, nt = tile / P.tiles_m;
+                const int m0 = mt * TC_BM;
+                const int n_img = m0 / pix_per_img;
+                const int h0 = (m0 - n_img * pix_per_img) / P.out_hw;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / P.cin_blocks, cb = kb - tap * P.cin_blocks;
+                    const TcTap tp = P.taps[tap];
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    const int c0 = tp.c_add + cb * TC_BK;
+                    tma_load_5d(st, &map_a_hi, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                    tma_load_2d(st + 2 * S::A_BYTES, &map_w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
+                    if (x3) {
+                        tma_load_5d(st + S::A_BYTES, &map_a_lo, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
+                    }
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ====================================== MMA issuer ======================================
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = F16, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
+                const uint32_t d1 = d0 + BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + S::A_BYTES);
+                    const uint64_t b_hi = make_sw128_desc(st + 2 * S::A_BYTES);
+                    const uint64_t b_lo = make_sw128_desc(st + 2 * S::A_BYTES + S::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // +32 bytes inside the swizzle row
+                        const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                        umma_f16(d0, a_hi + adv, b_hi + adv, idesc, accum);
+                        if (x3) {
+                            umma_f16(d1, a_hi + adv, b_lo + adv, idesc, accum);
+                            umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ======================================= epilogue =======================================
+        const int e = warp - 2;                 // 0..7
+        const int quarter = warp & 3;           // TMEM lanes this warp may touch: 32*quarter .. +31
+        const int half = e >> 2;                // which half of the tile's columns
+        constexpr int COLS = BN / 2;            // columns per warp
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile % P.tiles_m, nt = tile / P.tiles_m;
+            const int row = quarter * 32 + lane;
+            const long long m = (long long)mt * TC_BM + row;
+            const bool row_ok = m < P.M;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * COLS);
+#pragma unroll 1
+            for (int cc = 0; cc < COLS; cc += 32) {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(t_d0 + cc, r0);
+                if (x3) tmem_ld32(t_d0 + BN + cc, r1);
+                tmem_ld_wait();
+                const int n = nt * BN + half * COLS + cc;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float a = __uint_as_float(r0[j]);
+                    if (x3) a = fmaf(__uint_as_float(r1[j]), 1.0f / 2048.0f, a);
+                    v[j] = fmaf(a, __ldg(P.scale + n + j), __ldg(P.shift + n + j));
+                }
+                if (row_ok) {
+                    const size_t off = (size_t)m * P.Cout + n;
+                    if (P.res_hi) {
+                        const uint4* rh = reinterpret_cast<const uint4*>(P.res_hi + off);
+                        const uint4* rl = reinterpret_cast<const uint4*>(P.res_lo + off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 h4 = __ldg(rh + q);
+                            const uint4 l4 = x3 ? __ldg(rl + q) : make_uint4(0, 0, 0, 0);
+                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
+                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
+                                v[q * 8 + u * 2 + 0] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
+                                v[q * 8 + u * 2 + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
+                            }
+                        }
+                    }
+                    uint32_t oh[16], ol[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float a = v[j], b = v[j + 1];
+                        if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        a = fminf(fmaxf(a, -65504.f), 65504.f);          // fp16 range guard
+                        b = fminf(fmaxf(b, -65504.f), 65504.f);
+                        const __half2 h = __floats2half2_rn(a, b);
+                        const float2 hf = __half22float2(h);
+                        oh[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                        ol[j >> 1] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                    }
+                    uint4* ph = reinterpret_cast<uint4*>(P.out_hi + off);
+                    uint4* pl = reinterpret_cast<uint4*>(P.out_lo + off);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ph[q] = make_uint4(oh[q * 4], oh[q * 4 + 1], oh[q * 4 + 2], oh[q * 4 + 3]);
+                        pl[q] = make_uint4(ol[q * 4], ol[q * 4 + 1], ol[q * 4 + 2], ol[q * 4 + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable"); return IVOSW_ERR_CUDA; }
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+        set_error(buf);
+        return IVOSW_ERR_CUDA;
+    }
+    return IVOSW_OK;
+}
+
+// 5-d view of an NHWC fp16 activation plane whose boxes are "whole rows of the OUTPUT grid".
+static int encode_act_map(CUtensorMap* map, const __half* base, int B, int H, int C, int stride, int out_hw) {
+    const int W = H;
+    const int Wb = out_hw;
+    const int Hb = (TC_BM / Wb) < out_hw ? (TC_BM / Wb) : out_hw;
+    const int Nb = TC_BM / (Wb * Hb);
+    // (an 8x8 tile spans two images: with B == 1 the map claims a second image; the workspace behind it is
+    //  allocated and the rows it produces are never stored)
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)Wb, 1, (cuuint32_t)Hb, (cuuint32_t)Nb};
+    const cuuint64_t e = sizeof(__half);
+    if (stride == 1) {            // (C, W, 1, H, N)
+        dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B > Nb ? B : Nb;
+        strides[0] = (cuuint64_t)C * e; strides[1] = (cuuint64_t)W * C * e; strides[2] = (cuuint64_t)W * C * e;
+        strides[3] = (cuuint64_t)H * W * C * e;
+    } else {                      // (2C [w parity, c], W/2, 2 [h parity], H/2, N)
+        dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B > Nb ? B : Nb;
+        strides[0] = (cuuint64_t)2 * C * e; strides[1] = (cuuint64_t)W * C * e; strides[2] = (cuuint64_t)2 * W * C * e;
+        strides[3] = (cuuint64_t)H * W * C * e;
+    }
+    return encode_map(map, base, 5, dims, strides, box);
+}
+
+static int encode_w_map(CUtensorMap* map, const __half* base, int K, int Cout, int BN) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+    return encode_map(map, base, 2, dims, strides, box);
+}
+
+template <int BN>
+static int launch_tc_bn(ivosw_ctx* c, const CUtensorMap maps[4], const TcParams& P, cudaStream_t s) {
+    using S = TcSmem<BN>;
+    static bool attr = false;
+    if (!attr) {
+        IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr = true;
+    }
+    const int tiles = P.tiles_m * P.tiles_n;
+    const int grid = tiles < c->sm_count ? tiles : c->sm_count;
+    conv_tc_kernel<BN><<<grid, TC_THREADS, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], P);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const SplitAct* residual, const SplitAct& out,
+                   int B, int terms, cudaStream_t s) {
+    const int BN = L.cout >= 128 ? 128 : 64;
+    const int K = L.k * L.k * L.cin;
+    int rc;
+    CUtensorMap maps[4];
+    if ((rc = encode_act_map(&maps[0], in.hi, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
+    if ((rc = encode_act_map(&maps[1], in.lo, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
+    if ((rc = encode_w_map(&maps[2], L.w_hi, K, L.cout, BN))) return rc;
+    if ((rc = encode_w_map(&maps[3], L.w_lo, K, L.cout, BN))) return rc;
+    TcParams P;
+    memset(&P, 0, sizeof P);
+    P.M = B * L.out_hw * L.out_hw;
+    P.Cout = L.cout; P.Cin = L.cin;
+    P.num_taps = L.k * L.k; P.cin_blocks = L.cin / TC_BK;
+    P.out_hw = L.out_hw;
+    P.tiles_m = (P.M + TC_BM - 1) / TC_BM; P.tiles_n = L.cout / BN;
+    P.relu = L.relu ? 1 : 0; P.terms = terms;
+    P.scale = L.scale; P.shift = L.shift;
+    P.res_hi = residual ? residual->hi : nullptr; P.res_lo = residual ? residual->lo : nullptr;
+    P.out_hi = out.hi; P.out_lo = out.lo;
+    for (int kh = 0; kh < L.k; ++kh)
+        for (int kw = 0; kw < L.k; ++kw) {
+            TcTap& t = P.taps[kh * L.k + kw];
+            const int oy = kh - L.pad, ox = kw - L.pad;     // input offset of this tap relative to stride * out
+            if (L.stride == 1) {
+                t.c_add = 0; t.w_add = ox; t.p = 0; t.h_add = oy;
+            } else {                                        // ih = 2*oh + oy = 2*(oh + d) + parity
+                const int py = oy & 1, px = ox & 1;
+                t.p = py; t.h_add = (oy - py) / 2;
+                t.c_add = px * L.cin; t.w_add = (ox - px) / 2;
+            }
+        }
+    return BN == 128 ? launch_tc_bn<128>(c, maps, P, s) : launch_tc_bn<64>(c, maps, P, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers between the fp32 NHWC world (stem, probes) and the split-fp16 planes
+// ------------------------------------------------------------------------------------------------
+__global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                             long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= n) return;
+    float2 v = *reinterpret_cast<const float2*>(in + i);
+    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    __half2 h = __floats2half2_rn(v.x, v.y);
+    float2 hf = __half22float2(h);
+    *reinterpret_cast<__half2*>(hi + i) = h;
+    *reinterpret_cast<__half2*>(lo + i) = __floats2half2_rn((v.x - hf.x) * 2048.0f, (v.y - hf.y) * 2048.0f);
+}
+
+__global__ void merge_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out,
+                             long long n, int use_lo) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= n) return;
+    float2 h = __half22float2(*reinterpret_cast<const __half2*>(hi + i));
+    float2 l = use_lo ? __half22float2(*reinterpret_cast<const __half2*>(lo + i)) : make_float2(0.f, 0.f);
+    *reinterpret_cast<float2*>(out + i) = make_float2(fmaf(l.x, 1.0f / 2048.0f, h.x), fmaf(l.y, 1.0f / 2048.0f, h.y));
+}
+
+int launch_split(ivosw_ctx* c, const float* in, const SplitAct& out, long long n, cudaStream_t s) {
+    split_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, s>>>(in, out.hi, out.lo, n);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+int launch_merge(ivosw_ctx* c, const SplitAct& in, float* out, long long n, int use_lo, cudaStream_t s) {
+    merge_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, s>>>(in.hi, in.lo, out, n, use_lo);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+}  // namespace ivosw

@@ -71,6 +71,17 @@ struct DeviceBuffer {
     size_t bytes = 0;
 };
 
+// An activation tensor in split-fp16 form (conv_tc.cu): x = hi + lo / 2048, NHWC, two planes.
+struct SplitAct {
+    __half* hi;
+    __half* lo;
+};
+// The two planes share one DeviceBuffer sized for the fp32 tensor: hi in the first half, lo in the second.
+inline SplitAct split_view(const DeviceBuffer& b) {
+    return SplitAct{reinterpret_cast<__half*>(b.p),
+                    reinterpret_cast<__half*>(reinterpret_cast<char*>(b.p) + b.bytes / 2)};
+}
+
 }  // namespace ivosw
 
 struct ivosw_ctx {
@@ -136,6 +147,11 @@ int launch_stem(ivosw_ctx* c, int B, cudaStream_t s);
 // ---- conv_simt.cu
 int launch_conv_simt(ivosw_ctx* c, const ConvLayer& L, const float* in, const float* residual, float* out,
                      int B, cudaStream_t s);
+// ---- conv_tc.cu
+int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const SplitAct* residual, const SplitAct& out,
+                   int B, int terms, cudaStream_t s);
+int launch_split(ivosw_ctx* c, const float* in, const SplitAct& out, long long n, cudaStream_t s);
+int launch_merge(ivosw_ctx* c, const SplitAct& in, float* out, long long n, int use_lo, cudaStream_t s);
 // ---- head.cu
 int launch_gap_fc(ivosw_ctx* c, const float* r5, int B, float* scores, cudaStream_t s);
 int launch_object_mean(ivosw_ctx* c, const float* scores, int T, int O, const double* ann_dev, double* mq_dev,

@@ -238,6 +238,24 @@ class Engine:
         names = ("roi", "stem", "conv_stack", "head", "brain")
         return dict(zip(names, [float(v) for v in ms])), int(n.value)
 
+    # ------------------------------------------------------------------ test hook: one conv layer
+    def debug_conv_dims(self, layer_index):
+        d = (C.c_int * 6)()
+        check(lib.ivosw_debug_conv(self._h, layer_index, 0, None, None, None, 0, d, None))
+        return dict(zip(("cin", "in_hw", "cout", "out_hw", "k", "stride"), [int(v) for v in d]))
+
+    def debug_conv(self, layer_index, x_nhwc, residual_nhwc=None, conv_mode="simt_fp32"):
+        """x_nhwc: B x H x W x Cin CUDA fp32 -> B x OH x OW x Cout fp32 (BN + ReLU [+ residual] applied)."""
+        d = self.debug_conv_dims(layer_index)
+        x = self._dev32(x_nhwc)
+        B = x.shape[0]
+        assert tuple(x.shape[1:]) == (d["in_hw"], d["in_hw"], d["cin"])
+        res = self._dev32(residual_nhwc) if residual_nhwc is not None else None
+        out = torch.empty((B, d["out_hw"], d["out_hw"], d["cout"]), device=self.device, dtype=torch.float32)
+        check(lib.ivosw_debug_conv(self._h, layer_index, CONV_MODES[conv_mode], _ptr(x), _ptr(res), _ptr(out), B, None,
+                                   _stream(self.device)))
+        return out
+
     # ------------------------------------------------------------------ MANet tail (utils/utils_manet.py)
     def manet_tail(self, logits, H, W, masks_out=None, all_p_out=None, want_masks=True, want_probs=True):
         """logits: T x C x h x w CUDA fp32 -> (masks T x H x W fp32, all_P T x C x H x W fp32)."""
