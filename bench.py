@@ -302,7 +302,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--conv-mode", default=os.environ.get("IVOSW_CONV_MODE", "simt_fp32"),
+    ap.add_argument("--conv-mode", default=os.environ.get("IVOSW_CONV_MODE", "tc_fp16x3"),
                     choices=["simt_fp32", "tc_fp16x3", "tc_fp16x1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -12,7 +12,7 @@ from . import arch
 from ._lib import (BRAIN_NUM_PARAMS, CONV_SIMT_FP32, CONV_TC_FP16X1, CONV_TC_FP16X3, check, lib)
 
 CONV_MODES = {"simt_fp32": CONV_SIMT_FP32, "tc_fp16x3": CONV_TC_FP16X3, "tc_fp16x1": CONV_TC_FP16X1}
-DEFAULT_CONV_MODE = "simt_fp32"
+DEFAULT_CONV_MODE = "tc_fp16x3"
 
 
 def pack_brain(sd):

@@ -19,7 +19,7 @@ from ivosw import synth
 
 pytestmark = pytest.mark.gpu
 
-CONV_MODE = os.environ.get("IVOSW_CONV_MODE", "simt_fp32")
+CONV_MODE = os.environ.get("IVOSW_CONV_MODE", "tc_fp16x3")
 
 
 @pytest.fixture(scope="module")
