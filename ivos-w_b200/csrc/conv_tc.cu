@@ -157,29 +157,61 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// STAGED epilogue (the 1x1 "expand" layers, whose output + residual traffic dominates): the residual
+// tile arrives by TMA into a 128B-swizzled staging buffer, the epilogue rewrites it in place with the
+// output and a TMA store sends it back — deep memory-level parallelism and fully coalesced traffic
+// instead of per-thread 16-byte global accesses.
+template <int BN, int STAGES_, bool STAGED_>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (BN == 64) ? 4 : 3;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int STG_GROUP_BYTES = 2 * TC_BM * 64 * 2;   // hi + lo planes of a 128 x 64 half tile: 32 KB
+    static constexpr int STG_BYTES = STAGED_ ? 2 * STG_GROUP_BYTES : 0;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+    static constexpr int SS_OFF = BAR_OFF + 256;           // scale/shift staging: 2 groups x 128 floats
+    static constexpr int TOTAL = SS_OFF + 1024 + 1024 /*align slack*/;
 };
 
-template <int BN>
+struct TcMaps {
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;       // operands
+    CUtensorMap r_hi, r_lo, o_hi, o_lo;       // residual in / output (STAGED epilogue only)
+};
+
+template <int BN, int STAGES_, bool STAGED_>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-               const __grid_constant__ TcParams P) {
-    using S = TcSmem<BN>;
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
+    using S = TcSmem<BN, STAGES_, STAGED_>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* full_bar = bars;                       // [STAGES]
     uint64_t* empty_bar = bars + S::STAGES;          // [STAGES]
     uint64_t* tfull_bar = bars + 2 * S::STAGES;      // [2]
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2; // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+    uint64_t* res_bar = bars + 2 * S::STAGES + 4;    // [2] residual tile landed (STAGED)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = P.tiles_m * P.tiles_n;
@@ -188,9 +220,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     constexpr uint32_t TMEM_COLS = 4 * BN;           // 2 accumulator stages x (D0, D1)
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
         for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); mbar_init(&res_bar[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -203,6 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tiles are walked n-fastest: the CTAs that run together share A tiles (and all weights) in L2
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
@@ -210,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t tx_bytes = x3 ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
             const int pix_per_img = P.out_hw * P.out_hw;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mt = tile % P.tiles_m, nt = tile / P.tiles_m;
+                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const int m0 = mt * TC_BM;
                 const int n_img = m0 / pix_per_img;
                 const int h0 = (m0 - n_img * pix_per_img) / P.out_hw;
@@ -221,11 +256,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     const int c0 = tp.c_add + cb * TC_BK;
-                    tma_load_5d(st, &map_a_hi, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
-                    tma_load_2d(st + 2 * S::A_BYTES, &map_w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
+                    tma_load_5d(st, &maps.a_hi, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                    tma_load_2d(st + 2 * S::A_BYTES, &maps.w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
                     if (x3) {
-                        tma_load_5d(st + S::A_BYTES, &map_a_lo, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
-                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
+                        tma_load_5d(st + S::A_BYTES, &maps.a_lo, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
                     }
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -273,73 +308,167 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int quarter = warp & 3;           // TMEM lanes this warp may touch: 32*quarter .. +31
         const int half = e >> 2;                // which half of the tile's columns
         constexpr int COLS = BN / 2;            // columns per warp
+        const int row = quarter * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile % P.tiles_m, nt = tile / P.tiles_m;
-            const int row = quarter * 32 + lane;
-            const long long m = (long long)mt * TC_BM + row;
-            const bool row_ok = m < P.M;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * COLS);
+        if constexpr (STAGED_) {
+            static_assert(!STAGED_ || BN == 128, "staged epilogue is built for 128-column tiles");
+            const int gt = (e & 3) * 32 + lane;                 // thread index inside the 128-thread group
+            const bool leader = gt == 0;
+            const bool has_res = P.res_hi != nullptr;
+            uint8_t* stg = smem + S::STAGES * S::STAGE_BYTES + half * S::STG_GROUP_BYTES;
+            const uint32_t stg_hi = smem_u32(stg), stg_lo = stg_hi + TC_BM * 128;
+            float* ss = reinterpret_cast<float*>(smem + S::SS_OFF) + half * 128;
+            const uint32_t res_bytes = x3 ? 2u * TC_BM * 128 : 1u * TC_BM * 128;
+            uint32_t res_phase = 0;
+            if (leader && has_res && (int)blockIdx.x < num_tiles) {
+                const int nt = blockIdx.x % P.tiles_n, mt = blockIdx.x / P.tiles_n;
+                mbar_expect_tx(&res_bar[half], res_bytes);
+                tma_load_2d(stg, &maps.r_hi, &res_bar[half], nt * BN + half * 64, mt * TC_BM);
+                if (x3) tma_load_2d(stg + TC_BM * 128, &maps.r_lo, &res_bar[half], nt * BN + half * 64, mt * TC_BM);
+            }
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
+                const int n0g = nt * BN + half * 64;
+                ss[gt] = gt < 64 ? __ldg(P.scale + n0g + gt) : __ldg(P.shift + n0g + gt - 64);
+                group_bar(1 + half, 128);
+                if (has_res) { mbar_wait(&res_bar[half], res_phase); res_phase ^= 1; }
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * COLS);
 #pragma unroll 1
-            for (int cc = 0; cc < COLS; cc += 32) {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(t_d0 + cc, r0);
-                if (x3) tmem_ld32(t_d0 + BN + cc, r1);
-                tmem_ld_wait();
-                const int n = nt * BN + half * COLS + cc;
-                float v[32];
+                for (int cc = 0; cc < 64; cc += 32) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_d0 + cc, r0);
+                    if (x3) tmem_ld32(t_d0 + BN + cc, r1);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float a = __uint_as_float(r0[j]);
-                    if (x3) a = fmaf(__uint_as_float(r1[j]), 1.0f / 2048.0f, a);
-                    v[j] = fmaf(a, __ldg(P.scale + n + j), __ldg(P.shift + n + j));
-                }
-                if (row_ok) {
-                    const size_t off = (size_t)m * P.Cout + n;
-                    if (P.res_hi) {
-                        const uint4* rh = reinterpret_cast<const uint4*>(P.res_hi + off);
-                        const uint4* rl = reinterpret_cast<const uint4*>(P.res_lo + off);
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = (cc >> 3) + q;                                    // 16-byte chunk in the 128 B row
+                        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+                        float v[8];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 h4 = __ldg(rh + q);
-                            const uint4 l4 = x3 ? __ldg(rl + q) : make_uint4(0, 0, 0, 0);
+                        for (int k = 0; k < 8; ++k) {
+                            float a = __uint_as_float(r0[q * 8 + k]);
+                            if (x3) a = fmaf(__uint_as_float(r1[q * 8 + k]), 1.0f / 2048.0f, a);
+                            v[k] = fmaf(a, ss[cc + q * 8 + k], ss[64 + cc + q * 8 + k]);
+                        }
+                        if (has_res) {
+                            const uint4 h4 = lds128(stg_hi + off);
+                            const uint4 l4 = x3 ? lds128(stg_lo + off) : make_uint4(0, 0, 0, 0);
                             const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
                                 const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
-                                v[q * 8 + u * 2 + 0] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
-                                v[q * 8 + u * 2 + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
+                                v[u * 2 + 0] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
+                                v[u * 2 + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
                             }
                         }
-                    }
-                    uint32_t oh[16], ol[16];
+                        uint32_t oh[4], ol[4];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a = v[j], b = v[j + 1];
-                        if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                        a = fminf(fmaxf(a, -65504.f), 65504.f);          // fp16 range guard
-                        b = fminf(fmaxf(b, -65504.f), 65504.f);
-                        const __half2 h = __floats2half2_rn(a, b);
-                        const float2 hf = __half22float2(h);
-                        oh[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                        ol[j >> 1] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
-                    }
-                    uint4* ph = reinterpret_cast<uint4*>(P.out_hi + off);
-                    uint4* pl = reinterpret_cast<uint4*>(P.out_lo + off);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        ph[q] = make_uint4(oh[q * 4], oh[q * 4 + 1], oh[q * 4 + 2], oh[q * 4 + 3]);
-                        pl[q] = make_uint4(ol[q * 4], ol[q * 4 + 1], ol[q * 4 + 2], ol[q * 4 + 3]);
+                        for (int u = 0; u < 4; ++u) {
+                            float a = v[u * 2], b = v[u * 2 + 1];
+                            if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            a = fminf(fmaxf(a, -65504.f), 65504.f);
+                            b = fminf(fmaxf(b, -65504.f), 65504.f);
+                            const __half2 h = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h);
+                            oh[u] = *reinterpret_cast<const uint32_t*>(&h);
+                            ol[u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                        }
+                        sts128(stg_hi + off, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+                        sts128(stg_lo + off, make_uint4(ol[0], ol[1], ol[2], ol[3]));
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA store
+                group_bar(1 + half, 128);               // whole half tile staged
+                if (leader) {
+                    tma_store_2d(&maps.o_hi, stg, n0g, mt * TC_BM);
+                    tma_store_2d(&maps.o_lo, stg + TC_BM * 128, n0g, mt * TC_BM);
+                    bulk_commit();
+                    bulk_wait_read0();                  // staging buffer has been read
+                    const int next = tile + gridDim.x;
+                    if (has_res && next < num_tiles) {
+                        const int nnt = next % P.tiles_n, nmt = next / P.tiles_n;
+                        mbar_expect_tx(&res_bar[half], res_bytes);
+                        tma_load_2d(stg, &maps.r_hi, &res_bar[half], nnt * BN + half * 64, nmt * TC_BM);
+                        if (x3) tma_load_2d(stg + TC_BM * 128, &maps.r_lo, &res_bar[half], nnt * BN + half * 64, nmt * TC_BM);
+                    }
+                }
+                group_bar(1 + half, 128);               // staging buffer free for the next tile
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (leader) bulk_wait0();
+        } else {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
+                const long long m = (long long)mt * TC_BM + row;
+                const bool row_ok = m < P.M;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * COLS);
+#pragma unroll 1
+                for (int cc = 0; cc < COLS; cc += 32) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_d0 + cc, r0);
+                    if (x3) tmem_ld32(t_d0 + BN + cc, r1);
+                    tmem_ld_wait();
+                    const int n = nt * BN + half * COLS + cc;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float a = __uint_as_float(r0[j]);
+                        if (x3) a = fmaf(__uint_as_float(r1[j]), 1.0f / 2048.0f, a);
+                        v[j] = fmaf(a, __ldg(P.scale + n + j), __ldg(P.shift + n + j));
+                    }
+                    if (row_ok) {
+                        const size_t off = (size_t)m * P.Cout + n;
+                        if (P.res_hi) {
+                            const uint4* rh = reinterpret_cast<const uint4*>(P.res_hi + off);
+                            const uint4* rl = reinterpret_cast<const uint4*>(P.res_lo + off);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 h4 = __ldg(rh + q);
+                                const uint4 l4 = x3 ? __ldg(rl + q) : make_uint4(0, 0, 0, 0);
+                                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
+                                    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
+                                    v[q * 8 + u * 2 + 0] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
+                                    v[q * 8 + u * 2 + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
+                                }
+                            }
+                        }
+                        uint32_t oh[16], ol[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float a = v[j], b = v[j + 1];
+                            if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            a = fminf(fmaxf(a, -65504.f), 65504.f);          // fp16 range guard
+                            b = fminf(fmaxf(b, -65504.f), 65504.f);
+                            const __half2 h = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h);
+                            oh[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                            ol[j >> 1] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                        }
+                        uint4* ph = reinterpret_cast<uint4*>(P.out_hi + off);
+                        uint4* pl = reinterpret_cast<uint4*>(P.out_lo + off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            ph[q] = make_uint4(oh[q * 4], oh[q * 4 + 1], oh[q * 4 + 2], oh[q * 4 + 3]);
+                            pl[q] = make_uint4(ol[q * 4], ol[q * 4 + 1], ol[q * 4 + 2], ol[q * 4 + 3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
         }
     }
     tc_fence_before();
@@ -416,17 +545,26 @@ static int encode_w_map(CUtensorMap* map, const __half* base, int K, int Cout, i
     return encode_map(map, base, 2, dims, strides, box);
 }
 
-template <int BN>
-static int launch_tc_bn(ivosw_ctx* c, const CUtensorMap maps[4], const TcParams& P, cudaStream_t s) {
-    using S = TcSmem<BN>;
+static int encode_out_map(CUtensorMap* map, const __half* base, long long M, int Cout) {
+    cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)Cout * sizeof(__half)};
+    cuuint32_t box[2] = {64, (cuuint32_t)TC_BM};
+    return encode_map(map, base, 2, dims, strides, box);
+}
+
+template <int BN, int STAGES, bool STAGED>
+static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P, cudaStream_t s) {
+    using S = TcSmem<BN, STAGES, STAGED>;
+    static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
     static bool attr = false;
     if (!attr) {
-        IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        S::TOTAL));
         attr = true;
     }
     const int tiles = P.tiles_m * P.tiles_n;
     const int grid = tiles < c->sm_count ? tiles : c->sm_count;
-    conv_tc_kernel<BN><<<grid, TC_THREADS, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], P);
+    conv_tc_kernel<BN, STAGES, STAGED><<<grid, TC_THREADS, S::TOTAL, s>>>(maps, P);
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
@@ -436,15 +574,27 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
                    int B, int terms, cudaStream_t s) {
     const int BN = L.cout >= 128 ? 128 : 64;
     const int K = L.k * L.k * L.cin;
+    // the 1x1 "expand" layers (conv3 and downsample: Cout = 4 * planes) move the most output/residual bytes
+    const bool staged = (L.k == 1 && L.cout >= 256 && (residual != nullptr || L.is_downsample)) &&
+                        getenv("IVOSW_NO_STAGED_EPILOGUE") == nullptr;
     int rc;
-    CUtensorMap maps[4];
-    if ((rc = encode_act_map(&maps[0], in.hi, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
-    if ((rc = encode_act_map(&maps[1], in.lo, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
-    if ((rc = encode_w_map(&maps[2], L.w_hi, K, L.cout, BN))) return rc;
-    if ((rc = encode_w_map(&maps[3], L.w_lo, K, L.cout, BN))) return rc;
+    TcMaps maps;
+    memset(&maps, 0, sizeof maps);
     TcParams P;
     memset(&P, 0, sizeof P);
     P.M = B * L.out_hw * L.out_hw;
+    if ((rc = encode_act_map(&maps.a_hi, in.hi, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
+    if ((rc = encode_act_map(&maps.a_lo, in.lo, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
+    if ((rc = encode_w_map(&maps.w_hi, L.w_hi, K, L.cout, BN))) return rc;
+    if ((rc = encode_w_map(&maps.w_lo, L.w_lo, K, L.cout, BN))) return rc;
+    if (staged) {
+        if ((rc = encode_out_map(&maps.o_hi, out.hi, P.M, L.cout))) return rc;
+        if ((rc = encode_out_map(&maps.o_lo, out.lo, P.M, L.cout))) return rc;
+        if (residual) {
+            if ((rc = encode_out_map(&maps.r_hi, residual->hi, P.M, L.cout))) return rc;
+            if ((rc = encode_out_map(&maps.r_lo, residual->lo, P.M, L.cout))) return rc;
+        }
+    }
     P.Cout = L.cout; P.Cin = L.cin;
     P.num_taps = L.k * L.k; P.cin_blocks = L.cin / TC_BK;
     P.out_hw = L.out_hw;
@@ -465,7 +615,8 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
                 t.c_add = px * L.cin; t.w_add = (ox - px) / 2;
             }
         }
-    return BN == 128 ? launch_tc_bn<128>(c, maps, P, s) : launch_tc_bn<64>(c, maps, P, s);
+    if (staged) return launch_tc_variant<128, 2, true>(c, maps, P, s);
+    return BN == 128 ? launch_tc_variant<128, 3, false>(c, maps, P, s) : launch_tc_variant<64, 4, false>(c, maps, P, s);
 }
 
 // ------------------------------------------------------------------------------------------------
