@@ -233,7 +233,8 @@ def run_ours(args):
         step_e2e(i)
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
-    h2d = (b - a) * (3 + N_OBJ + 1) * HEIGHT * WIDTH * 4 + T_FRAMES * 8
+    # N=1: ivosw_round_host skips probability channel 0 (background, never read); N>1: torch copies of the shard
+    h2d = (b - a) * (3 + N_OBJ + (0 if world == 1 else 1)) * HEIGHT * WIDTH * 4 + T_FRAMES * 8
     d2h = T_FRAMES * (8 + 4) + 4
 
     if world > 1:

@@ -171,10 +171,23 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
             return rc;
         stage_end(c, tk, s);
         if ((rc = keep_probe(c, 0, (const float*)c->crop.p, (size_t)B * ROI * ROI * 4, s))) return rc;
+        const bool tc = c->conv_mode != IVOSW_CONV_SIMT_FP32;
+        const int terms = c->conv_mode == IVOSW_CONV_TC_FP16X3 ? 3 : 1;
+        SplitAct xs = split_view(c->c1);     // tensor-core path: pooled stem output as split-fp16 planes
         tk = stage_begin(c, 1, s);
-        if ((rc = launch_stem(c, B, s))) return rc;
+        if (tc) {
+            if ((rc = launch_stem_tc(c, B, xs, terms, s))) return rc;
+        } else {
+            if ((rc = launch_stem(c, B, s))) return rc;
+        }
         stage_end(c, tk, s);
-        if ((rc = keep_probe(c, 1, (const float*)c->pool.p, (size_t)B * 64 * 64 * 64, s))) return rc;
+        if (c->probes_on) {
+            const size_t n = (size_t)B * 64 * 64 * 64;
+            if (tc) {
+                if ((rc = ensure(c->probe_buf[1], n * sizeof(float)))) return rc;
+                if ((rc = launch_merge(c, xs, (float*)c->probe_buf[1].p, (long long)n, terms == 3, s))) return rc;
+            } else if ((rc = keep_probe(c, 1, (const float*)c->pool.p, n, s))) return rc;
+        }
         tk = stage_begin(c, 2, s);
         const long long launches_before = c->launches;
         const float* x = nullptr;      // fp32 NHWC r5 handed to the pooling/FC kernel
@@ -207,11 +220,8 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
             }
         } else {
             // tensor-core path: activations live as split-fp16 planes inside the same workspace buffers
-            const int terms = c->conv_mode == IVOSW_CONV_TC_FP16X3 ? 3 : 1;
             const SplitAct t1 = split_view(c->actT1), t2 = split_view(c->actT2), ds = split_view(c->actDS);
             const SplitAct outs[2] = {split_view(c->actX), split_view(c->actY)};
-            SplitAct xs = split_view(c->c1);     // c1 is free once the max-pool has run
-            if ((rc = launch_split(c, (const float*)c->pool.p, xs, (long long)B * 64 * 64 * 64, s))) return rc;
             int flip = 0, stage_probe = 2;
             for (size_t li = 0; li < c->layers.size(); ++li) {
                 const ConvLayer& L = c->layers[li];
@@ -304,6 +314,7 @@ void ivosw_destroy(ivosw_ctx* c) {
     if (c->stem_w) cudaFree(c->stem_w);
     if (c->stem_scale) cudaFree(c->stem_scale);
     if (c->stem_shift) cudaFree(c->stem_shift);
+    if (c->stem_wpack) cudaFree(c->stem_wpack);
     if (c->fc_w) cudaFree(c->fc_w);
     for (ConvLayer& L : c->layers) {
         if (L.w_f32) cudaFree(L.w_f32);
@@ -314,13 +325,14 @@ void ivosw_destroy(ivosw_ctx* c) {
     }
     DeviceBuffer* bufs[] = {&c->brain_gi, &c->brain_h, &c->brain_state, &c->brain_q, &c->brain_arg, &c->bbox_min,
                             &c->bbox_max, &c->boxes, &c->crop, &c->c1, &c->pool, &c->actX, &c->actY, &c->actDS,
-                            &c->actT1, &c->actT2, &c->scores, &c->mq, &c->stage_frames, &c->stage_probs};
+                            &c->actT1, &c->actT2, &c->scores, &c->scores_all, &c->mq, &c->stage_frames, &c->stage_probs};
     for (DeviceBuffer* b : bufs) release(*b);
     for (DeviceBuffer& b : c->probe_buf) release(b);
     drain_stage_events(c);
     for (cudaEvent_t e : c->evt_pool) cudaEventDestroy(e);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (cudaEvent_t e : c->chunk_evts) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -380,6 +392,7 @@ int ivosw_assess_load(ivosw_ctx* c, const float* blob, size_t n_floats) {
         for (int co = 0; co < 64; ++co)
             for (int k = 0; k < 196; ++k) wt[(size_t)k * 64 + co] = p[(size_t)co * 196 + k];
         if ((rc = upload(&c->stem_w, wt.data(), wt.size()))) return rc;
+        if ((rc = stem_tc_pack(c, p))) return rc;
         p += (size_t)64 * 196;
         std::vector<float> sc, sh;
         fold_bn(p, p + 64, p + 128, p + 192, 64, sc, sh);
@@ -444,7 +457,7 @@ int ivosw_assess_probe(ivosw_ctx* c, int which, float* out_dev, size_t capacity_
 // scoring half of a round for frames [t_begin, t_end): asynchronous, device outputs only
 static int score_shard(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
                        int t_begin, int t_end, const double* ann_dev, double* mq_dev, float* state_dev,
-                       float* scores_dev_out, cudaStream_t s) {
+                       float* scores_dev_out, int scores_pitch, cudaStream_t s) {
     const int Tl = t_end - t_begin;
     const long long HW = (long long)H * W;
     int rc;
@@ -457,9 +470,10 @@ static int score_shard(ivosw_ctx* c, const float* frames_dev, const float* probs
                                  ann_dev ? state_dev : nullptr, s)))
         return rc;
     stage_end(c, tk, s);
-    if (scores_dev_out)
-        IVOSW_CUDA(cudaMemcpyAsync(scores_dev_out, c->scores.p, sizeof(float) * (size_t)Tl * O,
-                                   cudaMemcpyDeviceToDevice, s));
+    if (scores_dev_out)   // [O][Tl] rows into a destination whose rows are scores_pitch floats apart
+        IVOSW_CUDA(cudaMemcpy2DAsync(scores_dev_out, sizeof(float) * (size_t)scores_pitch, c->scores.p,
+                                     sizeof(float) * (size_t)Tl, sizeof(float) * (size_t)Tl, O,
+                                     cudaMemcpyDeviceToDevice, s));
     return IVOSW_OK;
 }
 
@@ -470,10 +484,22 @@ static int timed_brain(ivosw_ctx* c, int T, cudaStream_t s) {
     return rc;
 }
 
-static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, int T, int O, int H, int W,
-                      int t_begin, int t_end, const double* ann_host, double* mq_host, float* scores_host,
-                      float* q_host, int* next_frame, cudaStream_t s) {
+static int e2e_chunk_frames() {
+    const char* e = getenv("IVOSW_E2E_CHUNK_FRAMES");
+    int v = e ? atoi(e) : 16;
+    return v < 1 ? 1 : v;
+}
+
+// One round over frames [t_begin, t_end).  With frames_host / probs_host set, the inputs are uploaded
+// into the context's staging buffers in frame chunks on a second stream, each chunk's scoring
+// waiting only for its own copy, so PCIe transfer and compute overlap; probability channel 0
+// (background) is never read by the path and is not transferred.
+static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_dev, const float* frames_host,
+                      const float* probs_host, int T, int O, int H, int W, int t_begin, int t_end,
+                      const double* ann_host, double* mq_host, float* scores_host, float* q_host, int* next_frame,
+                      cudaStream_t s) {
     const int Tl = t_end - t_begin;
+    const size_t HW = (size_t)H * W;
     int rc;
     // mq buffer: [Tl doubles mq][T doubles ann]
     if ((rc = ensure(c->mq, sizeof(double) * ((size_t)Tl + T)))) return rc;
@@ -494,9 +520,47 @@ static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_
     if (full && !c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
     memcpy(pin_ann, ann_host, sizeof(double) * T);
     IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, s));
-    if ((rc = score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, ann_dev, mq_dev,
-                          full ? (float*)c->brain_state.p : nullptr, nullptr, s)))
-        return rc;
+    const float* scores_src = (const float*)c->scores.p;
+    if (!frames_host) {
+        if ((rc = score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, ann_dev, mq_dev,
+                              full ? (float*)c->brain_state.p : nullptr, nullptr, 0, s)))
+            return rc;
+        scores_src = (const float*)c->scores.p;
+    } else {
+        const int FC = e2e_chunk_frames();
+        const int n_chunks = (Tl + FC - 1) / FC;
+        if (!c->copy_stream) IVOSW_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        while ((int)c->chunk_evts.size() < n_chunks + 1) {
+            cudaEvent_t e;
+            IVOSW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->chunk_evts.push_back(e);
+        }
+        if ((rc = ensure(c->stage_frames, sizeof(float) * (size_t)T * 3 * HW))) return rc;
+        if ((rc = ensure(c->stage_probs, sizeof(float) * (size_t)T * (O + 1) * HW))) return rc;
+        if (scores_host && (rc = ensure(c->scores_all, sizeof(float) * (size_t)Tl * O))) return rc;
+        float* fs = (float*)c->stage_frames.p;
+        float* ps = (float*)c->stage_probs.p;
+        // the copy stream must not overtake work already queued on s that may still read the staging buffers
+        IVOSW_CUDA(cudaEventRecord(c->chunk_evts[n_chunks], s));
+        IVOSW_CUDA(cudaStreamWaitEvent(c->copy_stream, c->chunk_evts[n_chunks], 0));
+        for (int ci = 0; ci < n_chunks; ++ci) {
+            const int c0 = t_begin + ci * FC, c1 = std::min(t_end, c0 + FC);
+            IVOSW_CUDA(cudaMemcpyAsync(fs + (size_t)c0 * 3 * HW, frames_host + (size_t)c0 * 3 * HW,
+                                       sizeof(float) * (size_t)(c1 - c0) * 3 * HW, cudaMemcpyHostToDevice,
+                                       c->copy_stream));
+            IVOSW_CUDA(cudaMemcpy2DAsync(ps + ((size_t)c0 * (O + 1) + 1) * HW, sizeof(float) * (size_t)(O + 1) * HW,
+                                         probs_host + ((size_t)c0 * (O + 1) + 1) * HW,
+                                         sizeof(float) * (size_t)(O + 1) * HW, sizeof(float) * (size_t)O * HW,
+                                         (size_t)(c1 - c0), cudaMemcpyHostToDevice, c->copy_stream));
+            IVOSW_CUDA(cudaEventRecord(c->chunk_evts[ci], c->copy_stream));
+            IVOSW_CUDA(cudaStreamWaitEvent(s, c->chunk_evts[ci], 0));
+            if ((rc = score_shard(c, fs, ps, T, O, H, W, c0, c1, nullptr, mq_dev + (c0 - t_begin), nullptr,
+                                  scores_host ? (float*)c->scores_all.p + (c0 - t_begin) : nullptr, Tl, s)))
+                return rc;
+        }
+        if (full && (rc = launch_pack_state(c, mq_dev, ann_dev, T, (float*)c->brain_state.p, s))) return rc;
+        scores_src = (const float*)c->scores_all.p;
+    }
     if (full) {
         if ((rc = timed_brain(c, T, s))) return rc;
         IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
@@ -504,7 +568,7 @@ static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_
     }
     IVOSW_CUDA(cudaMemcpyAsync(pin_mq, mq_dev, sizeof(double) * Tl, cudaMemcpyDeviceToHost, s));
     if (scores_host)
-        IVOSW_CUDA(cudaMemcpyAsync(pin_scores, c->scores.p, sizeof(float) * (size_t)Tl * O, cudaMemcpyDeviceToHost, s));
+        IVOSW_CUDA(cudaMemcpyAsync(pin_scores, scores_src, sizeof(float) * (size_t)Tl * O, cudaMemcpyDeviceToHost, s));
     IVOSW_CUDA(cudaStreamSynchronize(s));
     memcpy(mq_host, pin_mq, sizeof(double) * Tl);
     if (scores_host)   // device layout is [O][Tl]; the reference's mask_quality_pred is [Tl][O]
@@ -522,8 +586,8 @@ int ivosw_round_device(ivosw_ctx* c, const float* frames_dev, const float* probs
     IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 2 && W >= 2, "T, O, H, W");
     IVOSW_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= T, "frame range");
     IVOSW_CUDA(cudaSetDevice(c->device));
-    return round_core(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, ann_host, mq_host, scores_host, q_host,
-                      next_frame, (cudaStream_t)stream);
+    return round_core(c, frames_dev, probs_dev, nullptr, nullptr, T, O, H, W, t_begin, t_end, ann_host, mq_host,
+                      scores_host, q_host, next_frame, (cudaStream_t)stream);
 }
 
 int ivosw_round_host(ivosw_ctx* c, const float* frames_host, const float* probs_host, int T, int O, int H, int W,
@@ -532,17 +596,8 @@ int ivosw_round_host(ivosw_ctx* c, const float* frames_host, const float* probs_
     IVOSW_REQUIRE(c && frames_host && probs_host && ann_host && mq_host, "null pointer");
     IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 2 && W >= 2, "T, O, H, W");
     IVOSW_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t HW = (size_t)H * W;
-    int rc;
-    if ((rc = ensure(c->stage_frames, sizeof(float) * (size_t)T * 3 * HW))) return rc;
-    if ((rc = ensure(c->stage_probs, sizeof(float) * (size_t)T * (O + 1) * HW))) return rc;
-    IVOSW_CUDA(cudaMemcpyAsync(c->stage_frames.p, frames_host, sizeof(float) * (size_t)T * 3 * HW,
-                               cudaMemcpyHostToDevice, s));
-    IVOSW_CUDA(cudaMemcpyAsync(c->stage_probs.p, probs_host, sizeof(float) * (size_t)T * (O + 1) * HW,
-                               cudaMemcpyHostToDevice, s));
-    return round_core(c, (const float*)c->stage_frames.p, (const float*)c->stage_probs.p, T, O, H, W, 0, T, ann_host,
-                      mq_host, scores_host, q_host, next_frame, s);
+    return round_core(c, nullptr, nullptr, frames_host, probs_host, T, O, H, W, 0, T, ann_host, mq_host, scores_host,
+                      q_host, next_frame, (cudaStream_t)stream);
 }
 
 int ivosw_agent_action(ivosw_ctx* c, const double* mq_host, const double* ann_host, int T, float* q_host,
@@ -582,7 +637,7 @@ int ivosw_score_shard(ivosw_ctx* c, const float* frames_dev, const float* probs_
     IVOSW_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= T, "frame range");
     IVOSW_CUDA(cudaSetDevice(c->device));
     return score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, nullptr, mq_dev, nullptr, scores_dev,
-                       (cudaStream_t)stream);
+                       t_end - t_begin, (cudaStream_t)stream);
 }
 
 int ivosw_agent_action_dev(ivosw_ctx* c, const double* mq_dev, const double* ann_host, int T, float* q_host,

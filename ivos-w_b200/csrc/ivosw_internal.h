@@ -101,6 +101,7 @@ struct ivosw_ctx {
     float* stem_w = nullptr;         // [196][64]: (kh,kw,cin) x cout
     float* stem_scale = nullptr;
     float* stem_shift = nullptr;
+    void* stem_wpack = nullptr;      // stem weight as the smem image of stem_tc.cu (fp16 hi/lo planes)
     float mean[3], stdv[3];
     float* fc_w = nullptr;           // 2048
     float fc_b = 0.f;
@@ -123,7 +124,8 @@ struct ivosw_ctx {
     long long conv_launches_timed = 0;
 
     // host-staged rounds
-    ivosw::DeviceBuffer stage_frames, stage_probs;
+    ivosw::DeviceBuffer stage_frames, stage_probs, scores_all;
+    std::vector<cudaEvent_t> chunk_evts;
     void* pinned_small = nullptr;    // small pinned scratch for D2H results
     size_t pinned_small_bytes = 0;
     cudaStream_t copy_stream = nullptr;
@@ -144,6 +146,9 @@ int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStrea
 int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, cudaStream_t s);
 // ---- stem.cu
 int launch_stem(ivosw_ctx* c, int B, cudaStream_t s);
+// ---- stem_tc.cu
+int stem_tc_pack(ivosw_ctx* c, const float* w_ohwi);
+int launch_stem_tc(ivosw_ctx* c, int B, const SplitAct& out, int terms, cudaStream_t s);
 // ---- conv_simt.cu
 int launch_conv_simt(ivosw_ctx* c, const ConvLayer& L, const float* in, const float* residual, float* out,
                      int B, cudaStream_t s);

@@ -1,0 +1,58 @@
+"""Condenses `ncu -i rep --page raw --csv` of the 52 conv_tc launches of one round into a per-layer table:
+duration, tensor-pipe %, DRAM read/write bytes and throughput %, algorithmic bytes/FLOPs.
+usage: python profiles/summarise_ncu_raw.py raw.csv [B]"""
+import csv
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ivos-w_b200"))
+from ivosw import arch  # noqa: E402
+
+COLS = {
+    "t_us": "gpu__time_duration.sum",
+    "tensor": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "dram_rd": "dram__bytes_read.sum",
+    "dram_wr": "dram__bytes_write.sum",
+    "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "regs": "launch__registers_per_thread",
+    "warps": "sm__warps_active.avg.pct_of_peak_sustained_active",
+}
+
+
+def to_bytes(v, unit):
+    m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return float(v.replace(",", "")) * m.get(unit, 1)
+
+
+def main(path, B=128):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ix = {k: hdr.index(v) for k, v in COLS.items()}
+    name_i = hdr.index("Kernel Name")
+    specs = arch.resnet50_convs()
+    print("| # | layer | variant | us | tensor pipe % | DRAM rd MB | DRAM wr MB | DRAM % | alg MB (in+out+res+w) | alg TFLOP/s | traffic/alg |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|")
+    tot = {"t": 0.0, "rd": 0.0, "wr": 0.0, "alg": 0.0, "fl": 0.0, "tw": 0.0}
+    for i, (sp, r) in enumerate(zip(specs, rows[2:])):
+        t = float(r[ix["t_us"]].replace(",", ""))
+        tu = units[ix["t_us"]]
+        t_us = t / 1e3 if tu in ("ns", "nsecond") else (t if tu in ("us", "usecond") else t * 1e3)
+        rd = to_bytes(r[ix["dram_rd"]], units[ix["dram_rd"]])
+        wr = to_bytes(r[ix["dram_wr"]], units[ix["dram_wr"]])
+        fl = 2.0 * B * sp.out_hw ** 2 * sp.cout * sp.cin * sp.k * sp.k
+        alg = B * (sp.in_hw ** 2 * sp.cin + sp.out_hw ** 2 * sp.cout * (2 if sp.residual else 1)) * 4 + \
+            sp.cout * sp.cin * sp.k * sp.k * 4
+        tens = float(r[ix["tensor"]])
+        var = r[name_i].split("<")[-1].split(">")[0]
+        print("| %d | %s | %s | %.1f | %.1f | %.1f | %.1f | %s | %.1f | %.1f | %.2f |" %
+              (i, sp.name[8:], var, t_us, tens, rd / 1e6, wr / 1e6, r[ix["dram_pct"]], alg / 1e6, fl / t_us / 1e6,
+               (rd + wr) / alg))
+        tot["t"] += t_us; tot["rd"] += rd; tot["wr"] += wr; tot["alg"] += alg; tot["fl"] += fl; tot["tw"] += tens * t_us
+    print("\nconv stack: %.2f ms under ncu (cold cache, serialised); DRAM read %.2f GB + write %.2f GB = %.2f GB vs "
+          "algorithmic %.2f GB (x%.2f); time-weighted tensor pipe %.1f %%; algorithmic %.1f TFLOP/s" %
+          (tot["t"] / 1e3, tot["rd"] / 1e9, tot["wr"] / 1e9, (tot["rd"] + tot["wr"]) / 1e9, tot["alg"] / 1e9,
+           (tot["rd"] + tot["wr"]) / tot["alg"], tot["tw"] / tot["t"], tot["fl"] / tot["t"] / 1e6))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 128)

@@ -117,9 +117,12 @@ def test_round_vs_golden(eng, golden_dir, name):
     if T == 1 or q64[0] - q64[1] > 1e-6:
         assert r["next_frame"] == int(g["f32_next_frame"])
     # host-buffer entry point gives the same answer
-    rh = eng.round_host(torch.from_numpy(all_F), torch.from_numpy(all_P), synth.annotated_counts(annotated, T))
+    rh = eng.round_host(torch.from_numpy(all_F), torch.from_numpy(all_P), synth.annotated_counts(annotated, T),
+                        want_scores=True)
     assert rh["next_frame"] == r["next_frame"]
     np.testing.assert_array_equal(rh["mask_quality"], r["mask_quality"])
+    np.testing.assert_array_equal(rh["scores"], r["scores"])
+    np.testing.assert_array_equal(rh["q"], r["q"])
 
 
 def test_round_vs_oracle_480p(eng):
