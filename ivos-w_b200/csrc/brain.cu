@@ -133,7 +133,16 @@ __global__ void __launch_bounds__(512, 1) brain_recurrent_kernel(const float4* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// d1t: decoder_fc1.weight transposed to [256][128] (k-major) so the shared-memory image is a linear copy
+__global__ void brain_pack_d1t_kernel(const float* __restrict__ w, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 128 * 256, i = j * 256 + k
+    if (i >= 128 * 256) return;
+    int j = i >> 8, k = i & 255;
+    out[k * 128 + j] = w[i];
+}
+
 __global__ void __launch_bounds__(1024, 1) brain_decode_kernel(const float* __restrict__ P,
+                                                               const float4* __restrict__ d1t,
                                                                const float* __restrict__ Hout,  // [N][2][T][128]
                                                                int T, float* __restrict__ Q,     // [N][T]
                                                                int* __restrict__ argmax) {
@@ -142,10 +151,7 @@ __global__ void __launch_bounds__(1024, 1) brain_decode_kernel(const float* __re
     float* ss = sWt + 256 * 128;        // [8][256] relu'd concatenated state per group
     float* sred = ss + 8 * 256;         // [8][4]
     const int n = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < 128 * 256; i += 1024) {
-        int jj = i >> 8, k = i & 255;   // coalesced read of W[jj][k]
-        sWt[k * 128 + jj] = P[P_D1W + i];
-    }
+    for (int i = tid; i < 128 * 256 / 4; i += 1024) reinterpret_cast<float4*>(sWt)[i] = __ldg(d1t + i);
     const int g = tid >> 7, j = tid & 127, wig = (tid >> 5) & 3, lane = tid & 31;
     const float b1 = P[P_D1B + j], w2 = P[P_D2W + j], b2 = P[P_D2B];
     const float* hf = Hout + ((long long)n * 2 + 0) * T * 128;
@@ -197,7 +203,9 @@ __global__ void __launch_bounds__(1024, 1) brain_decode_kernel(const float* __re
 int brain_pack(ivosw_ctx* c) {
     if (!c->brain_whh_t) IVOSW_CUDA(cudaMalloc(&c->brain_whh_t, sizeof(float4) * 32 * 512));
     brain_pack_whh_kernel<<<(32 * 512 + 255) / 256, 256>>>(c->brain_params + P_WHH, (float4*)c->brain_whh_t);
-    c->launches += 1;
+    if (!c->brain_d1t) IVOSW_CUDA(cudaMalloc(&c->brain_d1t, sizeof(float) * 128 * 256));
+    brain_pack_d1t_kernel<<<(128 * 256 + 255) / 256, 256>>>(c->brain_params + P_D1W, c->brain_d1t);
+    c->launches += 2;
     IVOSW_CUDA(cudaGetLastError());
     const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
     const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
@@ -218,7 +226,8 @@ int launch_brain(ivosw_ctx* c, const float* state, int N, int T, float* q, int* 
                                                              (float*)c->brain_h.p);
     IVOSW_CUDA(cudaGetLastError());
     const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
-    brain_decode_kernel<<<N, 1024, dec_smem, s>>>(c->brain_params, (const float*)c->brain_h.p, T, q, argmax);
+    brain_decode_kernel<<<N, 1024, dec_smem, s>>>(c->brain_params, (const float4*)c->brain_d1t, (const float*)c->brain_h.p, T, q,
+                                                  argmax);
     IVOSW_CUDA(cudaGetLastError());
     c->launches += 3;
     return IVOSW_OK;

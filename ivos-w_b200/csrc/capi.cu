@@ -311,6 +311,7 @@ void ivosw_destroy(ivosw_ctx* c) {
     cudaDeviceSynchronize();
     if (c->brain_params) cudaFree(c->brain_params);
     if (c->brain_whh_t) cudaFree(c->brain_whh_t);
+    if (c->brain_d1t) cudaFree(c->brain_d1t);
     if (c->stem_w) cudaFree(c->stem_w);
     if (c->stem_scale) cudaFree(c->stem_scale);
     if (c->stem_shift) cudaFree(c->stem_shift);

@@ -93,6 +93,7 @@ struct ivosw_ctx {
     // Brain
     bool brain_loaded = false;
     float* brain_params = nullptr;   // canonical order, see header
+    float* brain_d1t = nullptr;      // decoder_fc1.weight transposed [256][128]
     float* brain_whh_t = nullptr;    // weight_hh transposed/packed for the recurrent kernel
     ivosw::DeviceBuffer brain_gi, brain_h, brain_state, brain_q, brain_arg;
 

@@ -113,11 +113,13 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* a_full = bars;          // builders -> MMA          (count 8: one arrive per builder warp)
-    uint64_t* a_empty = bars + 1;     // MMA -> builders          (tcgen05.commit)
-    uint64_t* t_full = bars + 2;      // [2] MMA -> epilogue
-    uint64_t* t_empty = bars + 4;     // [2] epilogue -> MMA      (count 4)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    // The A tile is built and consumed in two K parts (filter rows 0-3 = K steps 0-7, rows 4-6 = steps 8-13),
+    // each with its own full/empty pair, so building part 0 of the next c1 row overlaps the MMAs on part 1.
+    uint64_t* a_full = bars;          // [2] builders -> MMA      (count 4: one arrive per builder warp of the part)
+    uint64_t* a_empty = bars + 2;     // [2] MMA -> builders      (tcgen05.commit)
+    uint64_t* t_full = bars + 4;      // [2] MMA -> epilogue
+    uint64_t* t_empty = bars + 6;     // [2] epilogue -> MMA      (count 4)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool x3 = P.terms == 3;
 
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
     for (int i = threadIdx.x; i < 2 * B_PLANE / 16; i += THREADS)
         reinterpret_cast<uint4*>(smem + OFF_B)[i] = __ldg(P.wpack + i);
     if (threadIdx.x == 0) {
-        mb_init(a_full, 8); mb_init(a_empty, 1);
+        mb_init(&a_full[0], 4); mb_init(&a_full[1], 4); mb_init(&a_empty[0], 1); mb_init(&a_empty[1], 1);
         mb_init(&t_full[0], 1); mb_init(&t_full[1], 1); mb_init(&t_empty[0], 4); mb_init(&t_empty[1], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -151,21 +153,25 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
                 const int n_rows = 2 * rows_per_band + ((item % P.bands) == 0 ? 0 : 1);   // c1 rows of this band
                 for (int r = 0; r < n_rows; ++r) {
                     mb_wait(&t_empty[acc], acc_phase ^ 1);
-                    mb_wait(a_full, a_phase);
-                    tc_after();
                     const uint32_t d0 = tmem_base + (uint32_t)(acc * 128), d1 = d0 + 64;
 #pragma unroll 1
-                    for (int ks = 0; ks < KPAD / 16; ++ks) {
-                        // one K=16 step = two 8-element slabs: A slab stride 2048 B, B slab stride 1024 B
-                        const uint64_t da_hi = make_desc(a_hi + ks * 4096, 2048, 128), da_lo = make_desc(a_lo + ks * 4096, 2048, 128);
-                        const uint64_t db_hi = make_desc(b_hi + ks * 2048, 1024, 128), db_lo = make_desc(b_lo + ks * 2048, 1024, 128);
-                        mma_f16(d0, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
-                        if (x3) {
-                            mma_f16(d1, da_hi, db_lo, idesc, ks > 0 ? 1u : 0u);
-                            mma_f16(d1, da_lo, db_hi, idesc, 1u);
+                    for (int part = 0; part < 2; ++part) {
+                        mb_wait(&a_full[part], a_phase);
+                        tc_after();
+                        const int ks0 = part == 0 ? 0 : 8, ks1 = part == 0 ? 8 : KPAD / 16;
+#pragma unroll 1
+                        for (int ks = ks0; ks < ks1; ++ks) {
+                            // one K=16 step = two 8-element slabs: A slab stride 2048 B, B slab stride 1024 B
+                            const uint64_t da_hi = make_desc(a_hi + ks * 4096, 2048, 128), da_lo = make_desc(a_lo + ks * 4096, 2048, 128);
+                            const uint64_t db_hi = make_desc(b_hi + ks * 2048, 1024, 128), db_lo = make_desc(b_lo + ks * 2048, 1024, 128);
+                            mma_f16(d0, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+                            if (x3) {
+                                mma_f16(d1, da_hi, db_lo, idesc, ks > 0 ? 1u : 0u);
+                                mma_f16(d1, da_lo, db_hi, idesc, 1u);
+                            }
                         }
+                        mma_commit(&a_empty[part]);
                     }
-                    mma_commit(a_empty);
                     mma_commit(&t_full[acc]);
                     a_phase ^= 1;
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -174,8 +180,43 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
         }
     } else if (warp >= 8) {
         // ------------------------------------------------ A builders (256 threads)
+        // thread -> one c1 column (ow) and one K part: part 0 = filter rows 0..3, part 1 = rows 4..6.
+        // A filter row needs the 7 crop pixels 2*ow-3 .. 2*ow+3 (112 contiguous bytes); two filter rows
+        // (14 loads) are in flight at a time, and the first pair is issued before waiting for the slot.
         const int bt = threadIdx.x - 256;
+        const int ow = bt & 127, part = bt >> 7;
+        const int kh0 = part * 4, nkh = part == 0 ? 4 : 3;
+        const int ix0 = 2 * ow - 3;
         uint32_t e_phase = 0;
+        auto load_row = [&](const float4* im, int oh, int kh, float4* px) {
+            const int iy = 2 * oh - 3 + kh;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int ix = ix0 + j;
+                px[j] = (iy >= 0 && iy < ROI && ix >= 0 && ix < ROI) ? __ldg(im + iy * ROI + ix) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store_row = [&](int kh, const float4* px) {
+#pragma unroll
+            for (int sp = 0; sp < 4; ++sp) {              // slab = pixel pair (2sp, 2sp+1); the 8th pixel is zero pad
+                const float4 a4 = px[2 * sp];
+                const float4 b4 = sp < 3 ? px[2 * sp + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float v[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float a = fminf(fmaxf(v[2 * u], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * u + 1], -65504.f), 65504.f);
+                    const __half2 h = __floats2half2_rn(a, b);
+                    const float2 hf = __half22float2(h);
+                    hi[u] = *reinterpret_cast<const uint32_t*>(&h);
+                    lo[u] = pack2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                }
+                const int sl = kh * 4 + sp;
+                const uint32_t off = (uint32_t)((sl * 16 + (ow >> 3)) * 128 + (ow & 7) * 16);
+                *reinterpret_cast<uint4*>(smem + OFF_A + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (x3) *reinterpret_cast<uint4*>(smem + OFF_A + A_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        };
         for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
             const int img = item / P.bands, band = item % P.bands;
             const int p0 = band * rows_per_band;
@@ -184,34 +225,19 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
             const float4* im = P.crop + (size_t)img * ROI * ROI;
             for (int r = 0; r < n_rows; ++r) {
                 const int oh = r_first + r;
-                mb_wait(a_empty, e_phase ^ 1);
-                // 128 rows x 28 slabs; slab s: kh = s / 4, kw pair = 2 * (s % 4)
-                for (int i = bt; i < 128 * SLABS; i += 256) {
-                    const int ow = i & 127, s = i >> 7;
-                    const int kh = s >> 2, kw = (s & 3) * 2;
-                    const int iy = 2 * oh - 3 + kh, ix = 2 * ow - 3 + kw;
-                    float4 p0v = make_float4(0.f, 0.f, 0.f, 0.f), p1v = p0v;
-                    if (iy >= 0 && iy < ROI) {
-                        if (ix >= 0 && ix < ROI) p0v = __ldg(im + iy * ROI + ix);
-                        if (kw < 6 && ix + 1 >= 0 && ix + 1 < ROI) p1v = __ldg(im + iy * ROI + ix + 1);
-                    }
-                    const float v[8] = {p0v.x, p0v.y, p0v.z, p0v.w, p1v.x, p1v.y, p1v.z, p1v.w};
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float a = fminf(fmaxf(v[2 * u], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * u + 1], -65504.f), 65504.f);
-                        const __half2 h = __floats2half2_rn(a, b);
-                        const float2 hf = __half22float2(h);
-                        hi[u] = *reinterpret_cast<const uint32_t*>(&h);
-                        lo[u] = pack2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
-                    }
-                    const uint32_t off = (uint32_t)((s * 16 + (ow >> 3)) * 128 + (ow & 7) * 16);
-                    *reinterpret_cast<uint4*>(smem + OFF_A + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    if (x3) *reinterpret_cast<uint4*>(smem + OFF_A + A_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
+                float4 pa[7], pb[7];
+                load_row(im, oh, kh0, pa);
+                load_row(im, oh, kh0 + 1, pb);
+                mb_wait(&a_empty[part], e_phase ^ 1);
+                store_row(kh0, pa);
+                store_row(kh0 + 1, pb);
+                load_row(im, oh, kh0 + 2, pa);
+                if (nkh == 4) load_row(im, oh, kh0 + 3, pb);
+                store_row(kh0 + 2, pa);
+                if (nkh == 4) store_row(kh0 + 3, pb);
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mb_arrive(a_full);
+                if (lane == 0) mb_arrive(&a_full[part]);
                 e_phase ^= 1;
             }
         }
