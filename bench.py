@@ -49,8 +49,11 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load (B200_PROFILING.md).
+    Started before the warm-up; samples are attributed to the timed region by wall-clock window and,
+    when the timed region is shorter than a few sampling periods, the warm-up samples (same load)
+    are used as well."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -58,11 +61,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t_mark = [None, None]
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -71,28 +75,44 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, which):
+        self.t_mark[which] = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for nm, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def collect(rows):
+            sm, mx, reasons, pw = [], [], set(), []
+            for _, r in rows:
+                try:
+                    sm.append(float(r[2])); mx.append(float(r[3])); pw.append(float(r[4]))
+                except Exception:
+                    continue
+                for nm, v in zip(names, r[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, reasons, pw
+
+        t0, t1 = self.t_mark
+        timed = [x for x in self.rows if t0 is not None and t1 is not None and t0 <= x[0] <= t1 + 0.03]
+        window = "timed region"
+        if len(timed) < 3:
+            timed = [x for x in self.rows if t1 is None or x[0] <= t1 + 0.03]
+            window = "warm-up + timed region"
+        sm, mx, reasons, pw = collect(timed)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window,
+                "power_w_max": max(pw) if pw else None}
 
 
 def make_inputs(n_clips):
@@ -203,15 +223,19 @@ def run_ours(args):
         return float(ms.item())
 
     # ---- warm-up, then the timed region with clocks sampled under load
-    for i in range(max(3, args.warmup)):
-        step_device(i)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    for i in range(max(3, args.warmup)):
+        step_device(i)
     launches0 = eng.launch_count
     eng.stage_timing(True)
     eng.stage_times(reset=True)
+    if sampler:
+        sampler.mark(0)
     total_ms = timed(step_device, args.steps)
+    if sampler:
+        sampler.mark(1)
     stage_ms, n_conv = eng.stage_times(reset=True)
     eng.stage_timing(False)
     launches = eng.launch_count - launches0
@@ -224,17 +248,14 @@ def run_ours(args):
         Fh, Ph, ann = pin_clips[i % len(pin_clips)]
         if world == 1:
             return eng.round_host(Fh, Ph, ann)["next_frame"]
-        Fd, Pd, _ = dev_clips[i % len(dev_clips)]
-        Fd[a:b].copy_(Fh[a:b], non_blocking=True)
-        Pd[a:b].copy_(Ph[a:b], non_blocking=True)
-        return ivdist.sharded_round(eng, Fd, Pd, ann)[0]
+        return ivdist.sharded_round(eng, Fh, Ph, ann)[0]
 
     for i in range(2):
         step_e2e(i)
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
-    # N=1: ivosw_round_host skips probability channel 0 (background, never read); N>1: torch copies of the shard
-    h2d = (b - a) * (3 + N_OBJ + (0 if world == 1 else 1)) * HEIGHT * WIDTH * 4 + T_FRAMES * 8
+    # probability channel 0 (background) is never read by the path and is not transferred
+    h2d = (b - a) * (3 + N_OBJ) * HEIGHT * WIDTH * 4 + T_FRAMES * 8
     d2h = T_FRAMES * (8 + 4) + 4
 
     if world > 1:

@@ -156,6 +156,10 @@ IVOSW_API int ivosw_agent_action(ivosw_ctx* ctx, const double* mask_quality_host
 IVOSW_API int ivosw_score_shard(ivosw_ctx* ctx, const float* frames_dev, const float* probs_dev,
                       int T, int O, int H, int W, int t_begin, int t_end,
                       double* mq_dev, float* scores_dev, void* stream);
+/* ivosw_score_shard_host: as ivosw_score_shard, with the clip in HOST memory (full-clip base pointers;
+ * only frames [t_begin, t_end) are read): chunked upload overlapped with scoring.  Asynchronous. */
+IVOSW_API int ivosw_score_shard_host(ivosw_ctx* ctx, const float* frames_host, const float* probs_host,
+                           int T, int O, int H, int W, int t_begin, int t_end, double* mq_dev, void* stream);
 IVOSW_API int ivosw_agent_action_dev(ivosw_ctx* ctx, const double* mq_dev, const double* annotated_counts_host,
                            int T, float* q_host, int* next_frame, void* stream);
 

@@ -491,6 +491,50 @@ static int e2e_chunk_frames() {
     return v < 1 ? 1 : v;
 }
 
+// Scores frames [t_begin, t_end) whose inputs live in HOST memory: the frames and the O foreground
+// probability planes are uploaded into the context's staging buffers in chunks of a few frames on a
+// second stream; each chunk's scoring waits only for its own copy, so PCIe transfer and compute
+// overlap.  Probability channel 0 (background) is never read by the path and is not transferred.
+// mq_dev receives the float64 per-frame means; c->scores_all the per-object scores ([O][Tl]) on request.
+static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const float* probs_host, int T, int O,
+                                 int H, int W, int t_begin, int t_end, double* mq_dev, bool keep_scores,
+                                 cudaStream_t s) {
+    const int Tl = t_end - t_begin;
+    const size_t HW = (size_t)H * W;
+    int rc;
+    const int FC = e2e_chunk_frames();
+    const int n_chunks = (Tl + FC - 1) / FC;
+    if (!c->copy_stream) IVOSW_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    while ((int)c->chunk_evts.size() < n_chunks + 1) {
+        cudaEvent_t e;
+        IVOSW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_evts.push_back(e);
+    }
+    if ((rc = ensure(c->stage_frames, sizeof(float) * (size_t)T * 3 * HW))) return rc;
+    if ((rc = ensure(c->stage_probs, sizeof(float) * (size_t)T * (O + 1) * HW))) return rc;
+    if (keep_scores && (rc = ensure(c->scores_all, sizeof(float) * (size_t)Tl * O))) return rc;
+    float* fs = (float*)c->stage_frames.p;
+    float* ps = (float*)c->stage_probs.p;
+    // the copy stream must not overtake work already queued on s that may still read the staging buffers
+    IVOSW_CUDA(cudaEventRecord(c->chunk_evts[n_chunks], s));
+    IVOSW_CUDA(cudaStreamWaitEvent(c->copy_stream, c->chunk_evts[n_chunks], 0));
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int c0 = t_begin + ci * FC, c1 = std::min(t_end, c0 + FC);
+        IVOSW_CUDA(cudaMemcpyAsync(fs + (size_t)c0 * 3 * HW, frames_host + (size_t)c0 * 3 * HW,
+                                   sizeof(float) * (size_t)(c1 - c0) * 3 * HW, cudaMemcpyHostToDevice, c->copy_stream));
+        IVOSW_CUDA(cudaMemcpy2DAsync(ps + ((size_t)c0 * (O + 1) + 1) * HW, sizeof(float) * (size_t)(O + 1) * HW,
+                                     probs_host + ((size_t)c0 * (O + 1) + 1) * HW, sizeof(float) * (size_t)(O + 1) * HW,
+                                     sizeof(float) * (size_t)O * HW, (size_t)(c1 - c0), cudaMemcpyHostToDevice,
+                                     c->copy_stream));
+        IVOSW_CUDA(cudaEventRecord(c->chunk_evts[ci], c->copy_stream));
+        IVOSW_CUDA(cudaStreamWaitEvent(s, c->chunk_evts[ci], 0));
+        if ((rc = score_shard(c, fs, ps, T, O, H, W, c0, c1, nullptr, mq_dev + (c0 - t_begin), nullptr,
+                              keep_scores ? (float*)c->scores_all.p + (c0 - t_begin) : nullptr, Tl, s)))
+            return rc;
+    }
+    return IVOSW_OK;
+}
+
 // One round over frames [t_begin, t_end).  With frames_host / probs_host set, the inputs are uploaded
 // into the context's staging buffers in frame chunks on a second stream, each chunk's scoring
 // waiting only for its own copy, so PCIe transfer and compute overlap; probability channel 0
@@ -500,7 +544,6 @@ static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_
                       const double* ann_host, double* mq_host, float* scores_host, float* q_host, int* next_frame,
                       cudaStream_t s) {
     const int Tl = t_end - t_begin;
-    const size_t HW = (size_t)H * W;
     int rc;
     // mq buffer: [Tl doubles mq][T doubles ann]
     if ((rc = ensure(c->mq, sizeof(double) * ((size_t)Tl + T)))) return rc;
@@ -528,37 +571,9 @@ static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_
             return rc;
         scores_src = (const float*)c->scores.p;
     } else {
-        const int FC = e2e_chunk_frames();
-        const int n_chunks = (Tl + FC - 1) / FC;
-        if (!c->copy_stream) IVOSW_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        while ((int)c->chunk_evts.size() < n_chunks + 1) {
-            cudaEvent_t e;
-            IVOSW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->chunk_evts.push_back(e);
-        }
-        if ((rc = ensure(c->stage_frames, sizeof(float) * (size_t)T * 3 * HW))) return rc;
-        if ((rc = ensure(c->stage_probs, sizeof(float) * (size_t)T * (O + 1) * HW))) return rc;
-        if (scores_host && (rc = ensure(c->scores_all, sizeof(float) * (size_t)Tl * O))) return rc;
-        float* fs = (float*)c->stage_frames.p;
-        float* ps = (float*)c->stage_probs.p;
-        // the copy stream must not overtake work already queued on s that may still read the staging buffers
-        IVOSW_CUDA(cudaEventRecord(c->chunk_evts[n_chunks], s));
-        IVOSW_CUDA(cudaStreamWaitEvent(c->copy_stream, c->chunk_evts[n_chunks], 0));
-        for (int ci = 0; ci < n_chunks; ++ci) {
-            const int c0 = t_begin + ci * FC, c1 = std::min(t_end, c0 + FC);
-            IVOSW_CUDA(cudaMemcpyAsync(fs + (size_t)c0 * 3 * HW, frames_host + (size_t)c0 * 3 * HW,
-                                       sizeof(float) * (size_t)(c1 - c0) * 3 * HW, cudaMemcpyHostToDevice,
-                                       c->copy_stream));
-            IVOSW_CUDA(cudaMemcpy2DAsync(ps + ((size_t)c0 * (O + 1) + 1) * HW, sizeof(float) * (size_t)(O + 1) * HW,
-                                         probs_host + ((size_t)c0 * (O + 1) + 1) * HW,
-                                         sizeof(float) * (size_t)(O + 1) * HW, sizeof(float) * (size_t)O * HW,
-                                         (size_t)(c1 - c0), cudaMemcpyHostToDevice, c->copy_stream));
-            IVOSW_CUDA(cudaEventRecord(c->chunk_evts[ci], c->copy_stream));
-            IVOSW_CUDA(cudaStreamWaitEvent(s, c->chunk_evts[ci], 0));
-            if ((rc = score_shard(c, fs, ps, T, O, H, W, c0, c1, nullptr, mq_dev + (c0 - t_begin), nullptr,
-                                  scores_host ? (float*)c->scores_all.p + (c0 - t_begin) : nullptr, Tl, s)))
-                return rc;
-        }
+        if ((rc = score_range_from_host(c, frames_host, probs_host, T, O, H, W, t_begin, t_end, mq_dev,
+                                        scores_host != nullptr, s)))
+            return rc;
         if (full && (rc = launch_pack_state(c, mq_dev, ann_dev, T, (float*)c->brain_state.p, s))) return rc;
         scores_src = (const float*)c->scores_all.p;
     }
@@ -639,6 +654,16 @@ int ivosw_score_shard(ivosw_ctx* c, const float* frames_dev, const float* probs_
     IVOSW_CUDA(cudaSetDevice(c->device));
     return score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, nullptr, mq_dev, nullptr, scores_dev,
                        t_end - t_begin, (cudaStream_t)stream);
+}
+
+int ivosw_score_shard_host(ivosw_ctx* c, const float* frames_host, const float* probs_host, int T, int O, int H, int W,
+                           int t_begin, int t_end, double* mq_dev, void* stream) {
+    IVOSW_REQUIRE(c && frames_host && probs_host && mq_dev, "null pointer");
+    IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 2 && W >= 2, "T, O, H, W");
+    IVOSW_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= T, "frame range");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return score_range_from_host(c, frames_host, probs_host, T, O, H, W, t_begin, t_end, mq_dev, false,
+                                 (cudaStream_t)stream);
 }
 
 int ivosw_agent_action_dev(ivosw_ctx* c, const double* mq_dev, const double* ann_host, int T, float* q_host,

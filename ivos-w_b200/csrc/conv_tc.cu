@@ -32,8 +32,10 @@ namespace ivosw {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;           // fp16 elements per K block = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 320;
-constexpr int TC_EPI_WARPS = 8;
+// direct-epilogue variants: 2 + 8 warps; staged variant: 2 + 16 warps (its epilogue is issue-bound:
+// ~15 instructions per output element, so it gets four warps per TMEM lane quarter)
+__host__ __device__ constexpr int tc_threads(bool staged) { return staged ? 576 : 320; }
+__host__ __device__ constexpr int tc_epi_warps(bool staged) { return staged ? 16 : 8; }
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: no legitimate wait is this long
 
 struct TcTap { int c_add, w_add, p, h_add; };
@@ -136,6 +138,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row atoms of 1024 bytes)
@@ -177,10 +188,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// STAGED epilogue (the 1x1 "expand" layers, whose output + residual traffic dominates): the residual
-// tile arrives by TMA into a 128B-swizzled staging buffer, the epilogue rewrites it in place with the
-// output and a TMA store sends it back — deep memory-level parallelism and fully coalesced traffic
-// instead of per-thread 16-byte global accesses.
+// STAGED epilogue (the 1x1 "expand" layers, whose output + residual traffic dominates): per tile the
+// producer pushes one extra 64 KB block through the SAME shared-memory ring as the operand blocks — the
+// residual tile (hi/lo planes of both column halves, 128B-swizzled), prefetched by TMA while the
+// previous tile is still in its epilogue.  The epilogue groups rewrite that block in place with the
+// output, a TMA store sends it back, and the slot returns to the ring once the store has read it.
+// Deep memory-level parallelism and fully coalesced traffic instead of per-thread 16-byte accesses.
 template <int BN, int STAGES_, bool STAGED_>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
@@ -188,8 +201,8 @@ struct TcSmem {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = STAGES_;
     static constexpr int STG_GROUP_BYTES = 2 * TC_BM * 64 * 2;   // hi + lo planes of a 128 x 64 half tile: 32 KB
-    static constexpr int STG_BYTES = STAGED_ ? 2 * STG_GROUP_BYTES : 0;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+    static_assert(!STAGED_ || STAGE_BYTES == 2 * STG_GROUP_BYTES, "an epilogue block must fill exactly one ring slot");
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int SS_OFF = BAR_OFF + 256;           // scale/shift staging: 2 groups x 128 floats
     static constexpr int TOTAL = SS_OFF + 1024 + 1024 /*align slack*/;
 };
@@ -200,7 +213,7 @@ struct TcMaps {
 };
 
 template <int BN, int STAGES_, bool STAGED_>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(STAGED_), 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
     using S = TcSmem<BN, STAGES_, STAGED_>;
     extern __shared__ uint8_t smem_raw[];
@@ -221,9 +234,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
-        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        // staged variant: a slot is released by two arrivals (MMA commit + issuer, or the two epilogue leaders)
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], STAGED_ ? 2 : 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); mbar_init(&res_bar[i], 1);
+            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], tc_epi_warps(STAGED_)); mbar_init(&res_bar[i], 1);
         }
         fence_barrier_init();
     }
@@ -264,6 +278,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     }
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
+                if constexpr (STAGED_) {
+                    // epilogue block: residual tile of both column halves (or just the slot, for staging the output)
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    if (P.res_hi != nullptr) {
+                        mbar_expect_tx(&full_bar[stage], (x3 ? 4u : 2u) * TC_BM * 128);
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            tma_load_2d(st + g * S::STG_GROUP_BYTES, &maps.r_hi, &full_bar[stage], nt * BN + g * 64, m0);
+                            if (x3) tma_load_2d(st + g * S::STG_GROUP_BYTES + TC_BM * 128, &maps.r_lo, &full_bar[stage],
+                                                nt * BN + g * 64, m0);
+                        }
+                    } else {
+                        mbar_arrive(&full_bar[stage]);
+                    }
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -296,7 +327,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         }
                     }
                     umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
+                    if constexpr (STAGED_) mbar_arrive(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if constexpr (STAGED_) {
+                    // The tile's epilogue block is not ours, but we must see it land before moving on: a
+                    // parity test on this slot's NEXT use (an operand block, three positions later) would
+                    // otherwise pass prematurely while the residual TMA of this generation is still in flight.
+                    mbar_wait(&full_bar[stage], phase);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -312,45 +351,54 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         int acc = 0; uint32_t acc_phase = 0;
         if constexpr (STAGED_) {
             static_assert(!STAGED_ || BN == 128, "staged epilogue is built for 128-column tiles");
-            const int gt = (e & 3) * 32 + lane;                 // thread index inside the 128-thread group
+            // 16 warps: quarter = TMEM lane quarter, colq = which 32-column quarter of the 128-column tile;
+            // colq 0,1 form group 0 (columns 0..63, one 64-column TMA box), colq 2,3 group 1.
+            const int colq = e >> 2;
+            const int grp = colq >> 1;
+            const int gt = ((colq & 1) * 4 + (e & 3)) * 32 + lane;      // 0..255 inside the group
             const bool leader = gt == 0;
             const bool has_res = P.res_hi != nullptr;
-            uint8_t* stg = smem + S::STAGES * S::STAGE_BYTES + half * S::STG_GROUP_BYTES;
-            const uint32_t stg_hi = smem_u32(stg), stg_lo = stg_hi + TC_BM * 128;
-            float* ss = reinterpret_cast<float*>(smem + S::SS_OFF) + half * 128;
-            const uint32_t res_bytes = x3 ? 2u * TC_BM * 128 : 1u * TC_BM * 128;
-            uint32_t res_phase = 0;
-            if (leader && has_res && (int)blockIdx.x < num_tiles) {
-                const int nt = blockIdx.x % P.tiles_n, mt = blockIdx.x / P.tiles_n;
-                mbar_expect_tx(&res_bar[half], res_bytes);
-                tma_load_2d(stg, &maps.r_hi, &res_bar[half], nt * BN + half * 64, mt * TC_BM);
-                if (x3) tma_load_2d(stg + TC_BM * 128, &maps.r_lo, &res_bar[half], nt * BN + half * 64, mt * TC_BM);
-            }
+            const bool relu = P.relu != 0;
+            float* ss = reinterpret_cast<float*>(smem + S::SS_OFF) + grp * 128;   // [64 scale][64 shift]
+            int stage = 0; uint32_t phase = 0;                  // ring position, advanced in step with the producer
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
-                const int n0g = nt * BN + half * 64;
-                ss[gt] = gt < 64 ? __ldg(P.scale + n0g + gt) : __ldg(P.shift + n0g + gt - 64);
-                group_bar(1 + half, 128);
-                if (has_res) { mbar_wait(&res_bar[half], res_phase); res_phase ^= 1; }
+                const int n0g = nt * BN + grp * 64;
+                for (int kb = 0; kb < num_kb; ++kb)             // skip this tile's operand blocks
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                uint8_t* stg = smem + stage * S::STAGE_BYTES + grp * S::STG_GROUP_BYTES;
+                const uint32_t stg_hi = smem_u32(stg), stg_lo = stg_hi + TC_BM * 128;
+                if (gt < 128) ss[gt] = gt < 64 ? __ldg(P.scale + n0g + gt) : __ldg(P.shift + n0g + gt - 64);
+                group_bar(1 + grp, 256);
+                // Order matters: this role skips the operand blocks without waiting on them, so it may only
+                // test the epilogue block's barrier once the tile's MMAs are known to be complete — that
+                // guarantees every earlier use of the slot has finished and the parity test cannot alias
+                // with the previous generation of the barrier.
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * COLS);
-#pragma unroll 1
-                for (int cc = 0; cc < 64; cc += 32) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(t_d0 + cc, r0);
-                    if (x3) tmem_ld32(t_d0 + BN + cc, r1);
+                mbar_wait(&full_bar[stage], phase);             // residual landed / slot handed over
+                const int c0 = (colq & 1) * 32;                 // first column inside the group's 64
+                const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + colq * 32);
+#pragma unroll
+                for (int cc = 0; cc < 32; cc += 16) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(t_d0 + cc, r0);
+                    if (x3) tmem_ld16(t_d0 + BN + cc, r1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int j = (cc >> 3) + q;                                    // 16-byte chunk in the 128 B row
-                        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+                    for (int q = 0; q < 2; ++q) {
+                        const int col = c0 + cc + q * 8;                               // column inside the group's 64
+                        const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((col >> 3) ^ (row & 7)) << 4);
+                        const float4 s0 = *reinterpret_cast<const float4*>(ss + col), s1 = *reinterpret_cast<const float4*>(ss + col + 4);
+                        const float4 h0 = *reinterpret_cast<const float4*>(ss + 64 + col), h1 = *reinterpret_cast<const float4*>(ss + 64 + col + 4);
+                        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                         float v[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             float a = __uint_as_float(r0[q * 8 + k]);
                             if (x3) a = fmaf(__uint_as_float(r1[q * 8 + k]), 1.0f / 2048.0f, a);
-                            v[k] = fmaf(a, ss[cc + q * 8 + k], ss[64 + cc + q * 8 + k]);
+                            v[k] = fmaf(a, sc[k], sh[k]);
                         }
                         if (has_res) {
                             const uint4 h4 = lds128(stg_hi + off);
@@ -368,9 +416,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float a = v[u * 2], b = v[u * 2 + 1];
-                            if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                            a = fminf(fmaxf(a, -65504.f), 65504.f);
-                            b = fminf(fmaxf(b, -65504.f), 65504.f);
+                            if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            else { a = fmaxf(a, -65504.f); b = fmaxf(b, -65504.f); }
+                            a = fminf(a, 65504.f);                                      // fp16 range guard
+                            b = fminf(b, 65504.f);
                             const __half2 h = __floats2half2_rn(a, b);
                             const float2 hf = __half22float2(h);
                             oh[u] = *reinterpret_cast<const uint32_t*>(&h);
@@ -384,21 +433,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA store
-                group_bar(1 + half, 128);               // whole half tile staged
+                group_bar(1 + grp, 256);                // whole half tile staged (and ss no longer read)
                 if (leader) {
                     tma_store_2d(&maps.o_hi, stg, n0g, mt * TC_BM);
                     tma_store_2d(&maps.o_lo, stg + TC_BM * 128, n0g, mt * TC_BM);
                     bulk_commit();
-                    bulk_wait_read0();                  // staging buffer has been read
-                    const int next = tile + gridDim.x;
-                    if (has_res && next < num_tiles) {
-                        const int nnt = next % P.tiles_n, nmt = next / P.tiles_n;
-                        mbar_expect_tx(&res_bar[half], res_bytes);
-                        tma_load_2d(stg, &maps.r_hi, &res_bar[half], nnt * BN + half * 64, nmt * TC_BM);
-                        if (x3) tma_load_2d(stg + TC_BM * 128, &maps.r_lo, &res_bar[half], nnt * BN + half * 64, nmt * TC_BM);
-                    }
+                    bulk_wait_read0();                  // the store has read the slot
+                    mbar_arrive(&empty_bar[stage]);     // second leader's arrival returns it to the producer
                 }
-                group_bar(1 + half, 128);               // staging buffer free for the next tile
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (leader) bulk_wait0();
@@ -564,7 +607,7 @@ static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P
     }
     const int tiles = P.tiles_m * P.tiles_n;
     const int grid = tiles < c->sm_count ? tiles : c->sm_count;
-    conv_tc_kernel<BN, STAGES, STAGED><<<grid, TC_THREADS, S::TOTAL, s>>>(maps, P);
+    conv_tc_kernel<BN, STAGES, STAGED><<<grid, tc_threads(STAGED), S::TOTAL, s>>>(maps, P);
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
@@ -615,7 +658,7 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
                 t.c_add = px * L.cin; t.w_add = (ox - px) / 2;
             }
         }
-    if (staged) return launch_tc_variant<128, 2, true>(c, maps, P, s);
+    if (staged) return launch_tc_variant<128, 3, true>(c, maps, P, s);
     return BN == 128 ? launch_tc_variant<128, 3, false>(c, maps, P, s) : launch_tc_variant<64, 4, false>(c, maps, P, s);
 }
 

@@ -41,6 +41,8 @@ SYMBOLS = {
     "ivosw_agent_action": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, _c_i, C.c_void_p]),
     "ivosw_score_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ivosw_score_shard_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ivosw_agent_action_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, _c_i, C.c_void_p]),
     "ivosw_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ivosw_stage_times": (C.c_int, [C.c_void_p, _c_f, C.POINTER(C.c_longlong), C.c_int]),

@@ -36,7 +36,10 @@ def sharded_round(engine, all_F, all_P, annotated_counts, group=None):
     a, b = shard_range(T, world, rank)
     buf = torch.zeros(padded, dtype=torch.float64, device=engine.device)
     if b > a:
-        engine.score_shard(all_F, all_P, a, b, buf[rank * per: rank * per + (b - a)])
+        if all_F.is_cuda:
+            engine.score_shard(all_F, all_P, a, b, buf[rank * per: rank * per + (b - a)])
+        else:   # host-resident clip: chunked upload of this rank's shard, overlapped with its scoring
+            engine.score_shard_host(all_F, all_P, a, b, buf[rank * per: rank * per + (b - a)])
     if world > 1:
         dist.all_gather_into_tensor(buf, buf[rank * per:(rank + 1) * per].clone(), group=group)
     nf, q = engine.agent_action_dev(buf[:T], annotated_counts)

@@ -217,6 +217,16 @@ class Engine:
         check(lib.ivosw_score_shard(self._h, _ptr(all_F), _ptr(all_P), T, O, H, W, t_begin, t_end, _ptr(mq_out),
                                     _ptr(scores_out), _stream(self.device)))
 
+    def score_shard_host(self, all_F_host, all_P_host, t_begin, t_end, mq_out):
+        """As score_shard with the clip in host memory (CPU fp32 contiguous tensors, ideally pinned)."""
+        T, _, H, W = all_F_host.shape
+        O = all_P_host.shape[1] - 1
+        assert all_F_host.device.type == "cpu" and all_F_host.is_contiguous() and all_F_host.dtype == torch.float32
+        assert all_P_host.device.type == "cpu" and all_P_host.is_contiguous() and all_P_host.dtype == torch.float32
+        assert mq_out.dtype == torch.float64 and mq_out.is_cuda and mq_out.numel() == t_end - t_begin
+        check(lib.ivosw_score_shard_host(self._h, _ptr(all_F_host), _ptr(all_P_host), T, O, H, W, t_begin, t_end,
+                                         _ptr(mq_out), _stream(self.device)))
+
     def agent_action_dev(self, mq_dev, annotated_counts):
         """Brain + argmax on a device float64 quality vector (after the all-gather)."""
         T = mq_dev.numel()
