@@ -27,7 +27,7 @@ def main(path, round_index=2, B=128):
     print("| kernel | launches | total us | share |\n|---|---|---|---|")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("| %s | %d | %.1f | %.1f%% |" % (k[:70], a[0], a[1] / 1e3, 100 * a[1] / tot))
-    starts = [i for i, (k, v) in enumerate(seq) if "split_kernel" in k]
+    starts = [i for i, (k, v) in enumerate(seq) if "split_kernel" in k or "stem_tc_kernel" in k]
     if len(starts) <= round_index:
         return
     s = starts[round_index]
