@@ -226,19 +226,33 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    for i in range(max(3, args.warmup)):
+    # Per-stage CUDA-event timing (the roofline leg).  N == 1: recorded live inside the timed region (the
+    # library syncs once per round, so the events of every CUDA-graph replay are read back).  N > 1: the
+    # shard path is fully asynchronous, so the timed region runs untimed graphs and the stage times come
+    # from a second pass of the same steps.
+    live_stage_timing = world == 1
+    eng.stage_timing(live_stage_timing)
+    n_warm = max(4, args.warmup)          # every (clip, mode) CUDA graph is captured on its 2nd call
+    for i in range(n_warm):
         step_device(i)
     launches0 = eng.launch_count
-    eng.stage_timing(True)
     eng.stage_times(reset=True)
     if sampler:
         sampler.mark(0)
     total_ms = timed(step_device, args.steps)
     if sampler:
         sampler.mark(1)
+    launches = eng.launch_count - launches0
+    if not live_stage_timing:
+        eng.stage_timing(True)
+        for i in range(2):
+            step_device(i)
+        eng.stage_times(reset=True)
+        for i in range(args.steps):
+            step_device(i)
+        torch.cuda.synchronize()
     stage_ms, n_conv = eng.stage_times(reset=True)
     eng.stage_timing(False)
-    launches = eng.launch_count - launches0
     clocks = sampler.stop() if sampler else None
     ms_per_step = total_ms / args.steps
     value = T_FRAMES * 1e3 / ms_per_step
@@ -299,11 +313,13 @@ def run_ours(args):
 
     line = {
         "metric": "frames/sec per interaction round", "value": value, "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(4, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "conv_mode": args.conv_mode, "frames_per_gpu": b - a,
                    "parallelism": "frame-shard x%d + 1 all-gather" % world if world > 1 else "single GPU",
-                   "l2": "inputs (630 MB per clip, 2 clips alternating) exceed the 126 MB L2"},
+                   "l2": "inputs (630 MB per clip, 2 clips alternating) exceed the 126 MB L2",
+                   "launch": "CUDA-graph replay of the round (captured on the 2nd call per clip)",
+                   "stage_timing": "live in the timed region" if world == 1 else "separate pass of the same steps"},
         "clocks": clocks,
         "e2e": {"value": T_FRAMES * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},

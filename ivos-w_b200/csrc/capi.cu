@@ -26,8 +26,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return IVOSW_ERR_CUDA;
 }
 
+// bumped whenever a workspace buffer moves: captured CUDA graphs hold raw pointers and must be rebuilt
+static unsigned long long g_alloc_epoch = 1;
+
 int ensure(DeviceBuffer& b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return IVOSW_OK;
+    ++g_alloc_epoch;
     if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
     size_t want = (bytes + 255) & ~(size_t)255;
     IVOSW_CUDA(cudaMalloc(&b.p, want));
@@ -50,16 +54,35 @@ static cudaEvent_t take_event(ivosw_ctx* c) {
 int stage_begin(ivosw_ctx* c, int stage, cudaStream_t s) {
     if (!c->timing_on) return -1;
     ivosw_ctx::StageEvt ev{stage, take_event(c), take_event(c)};
+    if (c->capturing) {   // external record node: the event is re-recorded by every replay and can be timed
+        cudaEventRecordWithFlags(ev.a, s, cudaEventRecordExternal);
+        c->capture_evts->push_back(ev);
+        return (int)c->capture_evts->size() - 1;
+    }
     cudaEventRecord(ev.a, s);
     c->stage_evts.push_back(ev);
     return (int)c->stage_evts.size() - 1;
 }
 
 void stage_end(ivosw_ctx* c, int idx, cudaStream_t s) {
-    if (idx >= 0) cudaEventRecord(c->stage_evts[idx].b, s);
+    if (idx < 0) return;
+    if (c->capturing) cudaEventRecordWithFlags((*c->capture_evts)[idx].b, s, cudaEventRecordExternal);
+    else cudaEventRecord(c->stage_evts[idx].b, s);
+}
+
+// timing events of the graph replayed last (must be read before that graph is launched again)
+static void drain_graph_events(ivosw_ctx* c) {
+    if (!c->last_graph) return;
+    for (auto& ev : c->last_graph->evts) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.b) == cudaSuccess && cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess)
+            c->stage_ms[ev.stage] += ms;
+    }
+    c->last_graph = nullptr;
 }
 
 static void drain_stage_events(ivosw_ctx* c) {
+    drain_graph_events(c);
     for (auto& ev : c->stage_evts) {
         float ms = 0.f;
         if (cudaEventSynchronize(ev.b) == cudaSuccess && cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess)
@@ -268,8 +291,82 @@ static int ensure_pinned(ivosw_ctx* c, size_t bytes) {
     if (c->pinned_small_bytes >= bytes) return IVOSW_OK;
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     c->pinned_small = nullptr; c->pinned_small_bytes = 0;
+    ++g_alloc_epoch;
     IVOSW_CUDA(cudaMallocHost(&c->pinned_small, bytes));
     c->pinned_small_bytes = bytes;
+    return IVOSW_OK;
+}
+
+static bool same_key(const ivosw_ctx::GraphKey& a, const ivosw_ctx::GraphKey& b) { return memcmp(&a, &b, sizeof a) == 0; }
+
+static void drop_graph(ivosw_ctx* c, ivosw_ctx::GraphEntry& e) {
+    if (c->last_graph == &e) drain_graph_events(c);
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+    e.exec = nullptr;
+    for (auto& ev : e.evts) { c->evt_pool.push_back(ev.a); c->evt_pool.push_back(ev.b); }
+    e.evts.clear();
+    e.seen = 0;
+}
+
+// Runs `fn(stream)` (which only ENQUEUES work) either eagerly or — from the second identical call on —
+// as a replay of a CUDA graph captured from it.  First call: eager (it also performs every
+// allocation); second call: stream capture + instantiate; afterwards: one cudaGraphLaunch per call.
+// Graphs are rebuilt whenever a workspace buffer has moved since the capture.
+template <class F>
+static int run_graphed(ivosw_ctx* c, ivosw_ctx::GraphKey key, cudaStream_t s, F&& fn) {
+    if (!c->graphs_on || c->probes_on) return fn(s);
+    key.flags |= c->timing_on ? 0x100 : 0;
+    ivosw_ctx::GraphEntry* e = nullptr;
+    for (auto& g : c->graphs) if (same_key(g.key, key)) { e = &g; break; }
+    if (e && e->epoch != g_alloc_epoch) { drop_graph(c, *e); }
+    if (!e) {
+        if (c->graphs.size() >= 64) { for (auto& g : c->graphs) drop_graph(c, g); c->graphs.clear(); }
+        c->graphs.reserve(64);     // entries are referenced by pointer (last_graph): never reallocate
+        c->graphs.emplace_back();
+        e = &c->graphs.back();
+        e->key = key;
+    }
+    if (e->seen == 0) {
+        const int rc = fn(s);
+        e->seen = 1; e->epoch = g_alloc_epoch;
+        return rc;
+    }
+    if (!e->exec) {
+        if (!c->graph_stream) {
+            IVOSW_CUDA(cudaStreamCreate(&c->graph_stream));
+            IVOSW_CUDA(cudaEventCreateWithFlags(&c->g_ev1, cudaEventDisableTiming));
+            IVOSW_CUDA(cudaEventCreateWithFlags(&c->g_ev2, cudaEventDisableTiming));
+        }
+        const unsigned long long epoch0 = g_alloc_epoch;
+        const long long l0 = c->launches, cl0 = c->conv_launches_timed;
+        IVOSW_CUDA(cudaStreamBeginCapture(c->graph_stream, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true; c->capture_evts = &e->evts;
+        const int rc = fn(c->graph_stream);
+        c->capturing = false; c->capture_evts = nullptr;
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(c->graph_stream, &g);
+        e->launches = c->launches - l0; e->conv_launches = c->conv_launches_timed - cl0;
+        c->launches = l0; c->conv_launches_timed = cl0;
+        if (rc != IVOSW_OK || ce != cudaSuccess || g == nullptr || epoch0 != g_alloc_epoch) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            drop_graph(c, *e);
+            if (rc != IVOSW_OK) return rc;
+            return fn(s);           // could not capture (e.g. a buffer had to grow): run eagerly
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&e->exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) { e->exec = nullptr; cudaGetLastError(); drop_graph(c, *e); return fn(s); }
+        e->epoch = g_alloc_epoch;
+    }
+    if (c->last_graph) drain_graph_events(c);       // never overwrite unread timing events
+    IVOSW_CUDA(cudaEventRecord(c->g_ev1, s));
+    IVOSW_CUDA(cudaStreamWaitEvent(c->graph_stream, c->g_ev1, 0));
+    IVOSW_CUDA(cudaGraphLaunch(e->exec, c->graph_stream));
+    IVOSW_CUDA(cudaEventRecord(c->g_ev2, c->graph_stream));
+    IVOSW_CUDA(cudaStreamWaitEvent(s, c->g_ev2, 0));
+    c->launches += e->launches;
+    if (c->timing_on) { c->conv_launches_timed += e->conv_launches; c->last_graph = e; }
     return IVOSW_OK;
 }
 
@@ -300,6 +397,7 @@ int ivosw_create(int device, int conv_mode, ivosw_ctx** out) {
     c->conv_mode = conv_mode;
     c->sm_count = prop.multiProcessorCount;
     c->chunk_cap = chunk_cap_default();
+    { const char* g = getenv("IVOSW_GRAPHS"); c->graphs_on = !(g && atoi(g) == 0); }
     c->layers = make_resnet50_layers();
     *out = c;
     return IVOSW_OK;
@@ -329,6 +427,11 @@ void ivosw_destroy(ivosw_ctx* c) {
                             &c->actT1, &c->actT2, &c->scores, &c->scores_all, &c->mq, &c->stage_frames, &c->stage_probs};
     for (DeviceBuffer* b : bufs) release(*b);
     for (DeviceBuffer& b : c->probe_buf) release(b);
+    for (auto& g : c->graphs) drop_graph(c, g);
+    c->graphs.clear();
+    if (c->graph_stream) cudaStreamDestroy(c->graph_stream);
+    if (c->g_ev1) cudaEventDestroy(c->g_ev1);
+    if (c->g_ev2) cudaEventDestroy(c->g_ev2);
     drain_stage_events(c);
     for (cudaEvent_t e : c->evt_pool) cudaEventDestroy(e);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
@@ -426,6 +529,7 @@ int ivosw_assess_load(ivosw_ctx* c, const float* blob, size_t n_floats) {
     if ((rc = upload(&c->fc_w, p, 2048))) return rc;
     c->fc_b = p[2048];
     c->assess_loaded = true;
+    ++g_alloc_epoch;   // scalars (fc bias, mean, std) are baked into captured kernel arguments
     return IVOSW_OK;
 }
 
@@ -563,29 +667,47 @@ static int round_core(ivosw_ctx* c, const float* frames_dev, const float* probs_
     const bool full = (t_begin == 0 && t_end == T) && (q_host || next_frame);
     if (full && !c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
     memcpy(pin_ann, ann_host, sizeof(double) * T);
-    IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, s));
-    const float* scores_src = (const float*)c->scores.p;
     if (!frames_host) {
-        if ((rc = score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, ann_dev, mq_dev,
-                              full ? (float*)c->brain_state.p : nullptr, nullptr, 0, s)))
-            return rc;
-        scores_src = (const float*)c->scores.p;
+        // device-resident inputs: the whole round is one enqueue-only sequence -> CUDA-graph replay
+        if ((rc = ensure(c->scores, sizeof(float) * (size_t)Tl * O))) return rc;
+        auto enqueue = [&](cudaStream_t st) -> int {
+            int r;
+            IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+            if ((r = score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, ann_dev, mq_dev,
+                                 full ? (float*)c->brain_state.p : nullptr, nullptr, 0, st)))
+                return r;
+            if (full) {
+                if ((r = timed_brain(c, T, st))) return r;
+                IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, st));
+                IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            }
+            IVOSW_CUDA(cudaMemcpyAsync(pin_mq, mq_dev, sizeof(double) * Tl, cudaMemcpyDeviceToHost, st));
+            if (scores_host)
+                IVOSW_CUDA(cudaMemcpyAsync(pin_scores, c->scores.p, sizeof(float) * (size_t)Tl * O,
+                                           cudaMemcpyDeviceToHost, st));
+            return IVOSW_OK;
+        };
+        ivosw_ctx::GraphKey key{frames_dev, probs_dev, nullptr, T, O, H, W, t_begin, t_end, c->conv_mode, 1,
+                                (full ? 1 : 0) | (scores_host ? 2 : 0)};
+        if ((rc = run_graphed(c, key, s, enqueue))) return rc;
     } else {
+        IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, s));
         if ((rc = score_range_from_host(c, frames_host, probs_host, T, O, H, W, t_begin, t_end, mq_dev,
                                         scores_host != nullptr, s)))
             return rc;
         if (full && (rc = launch_pack_state(c, mq_dev, ann_dev, T, (float*)c->brain_state.p, s))) return rc;
-        scores_src = (const float*)c->scores_all.p;
+        if (full) {
+            if ((rc = timed_brain(c, T, s))) return rc;
+            IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
+            IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        }
+        IVOSW_CUDA(cudaMemcpyAsync(pin_mq, mq_dev, sizeof(double) * Tl, cudaMemcpyDeviceToHost, s));
+        if (scores_host)
+            IVOSW_CUDA(cudaMemcpyAsync(pin_scores, c->scores_all.p, sizeof(float) * (size_t)Tl * O,
+                                       cudaMemcpyDeviceToHost, s));
     }
-    if (full) {
-        if ((rc = timed_brain(c, T, s))) return rc;
-        IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
-        IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    }
-    IVOSW_CUDA(cudaMemcpyAsync(pin_mq, mq_dev, sizeof(double) * Tl, cudaMemcpyDeviceToHost, s));
-    if (scores_host)
-        IVOSW_CUDA(cudaMemcpyAsync(pin_scores, scores_src, sizeof(float) * (size_t)Tl * O, cudaMemcpyDeviceToHost, s));
     IVOSW_CUDA(cudaStreamSynchronize(s));
+    drain_graph_events(c);
     memcpy(mq_host, pin_mq, sizeof(double) * Tl);
     if (scores_host)   // device layout is [O][Tl]; the reference's mask_quality_pred is [Tl][O]
         for (int t = 0; t < Tl; ++t)
@@ -652,8 +774,17 @@ int ivosw_score_shard(ivosw_ctx* c, const float* frames_dev, const float* probs_
     IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 2 && W >= 2, "T, O, H, W");
     IVOSW_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= T, "frame range");
     IVOSW_CUDA(cudaSetDevice(c->device));
-    return score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, nullptr, mq_dev, nullptr, scores_dev,
-                       t_end - t_begin, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    auto enqueue = [&](cudaStream_t st) -> int {
+        return score_shard(c, frames_dev, probs_dev, T, O, H, W, t_begin, t_end, nullptr, mq_dev, nullptr, scores_dev,
+                           t_end - t_begin, st);
+    };
+    // (no host synchronisation here, so per-replay timing events could not be read back: eager when timing)
+    if (c->timing_on || scores_dev) return enqueue(s);
+    int rc;
+    if ((rc = ensure(c->scores, sizeof(float) * (size_t)(t_end - t_begin) * O))) return rc;
+    ivosw_ctx::GraphKey key{frames_dev, probs_dev, mq_dev, T, O, H, W, t_begin, t_end, c->conv_mode, 2, 0};
+    return run_graphed(c, key, s, enqueue);
 }
 
 int ivosw_score_shard_host(ivosw_ctx* c, const float* frames_host, const float* probs_host, int T, int O, int H, int W,
@@ -684,12 +815,21 @@ int ivosw_agent_action_dev(ivosw_ctx* c, const double* mq_dev, const double* ann
     int* pin_arg = (int*)(pin_q + T);
     double* ann_dev = (double*)c->mq.p + T;   // second half of the mq buffer (first half may be mq_dev itself)
     memcpy(pin_ann, ann_host, sizeof(double) * T);
-    IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, s));
-    if ((rc = launch_pack_state(c, mq_dev, ann_dev, T, (float*)c->brain_state.p, s))) return rc;
-    if ((rc = timed_brain(c, T, s))) return rc;
-    IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
-    IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if ((rc = ensure(c->brain_gi, sizeof(float) * (size_t)T * 512))) return rc;
+    if ((rc = ensure(c->brain_h, sizeof(float) * (size_t)2 * T * 128))) return rc;
+    auto enqueue = [&](cudaStream_t st) -> int {
+        int r;
+        IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+        if ((r = launch_pack_state(c, mq_dev, ann_dev, T, (float*)c->brain_state.p, st))) return r;
+        if ((r = timed_brain(c, T, st))) return r;
+        IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, st));
+        IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        return IVOSW_OK;
+    };
+    ivosw_ctx::GraphKey key{mq_dev, nullptr, nullptr, T, 0, 0, 0, 0, 0, 0, 3, 0};
+    if ((rc = run_graphed(c, key, s, enqueue))) return rc;
     IVOSW_CUDA(cudaStreamSynchronize(s));
+    drain_graph_events(c);
     if (q_host) memcpy(q_host, pin_q, sizeof(float) * T);
     if (next_frame) *next_frame = *pin_arg;
     return IVOSW_OK;

@@ -124,6 +124,27 @@ struct ivosw_ctx {
     float stage_ms[IVOSW_NUM_STAGES] = {0, 0, 0, 0, 0};
     long long conv_launches_timed = 0;
 
+    // CUDA-graph replay of whole rounds / shards (capi.cu: run_graphed)
+    struct GraphKey {
+        const void* p0; const void* p1; const void* p2;
+        int T, O, H, W, tb, te, mode, kind, flags;
+    };
+    struct GraphEntry {
+        GraphKey key;
+        unsigned long long epoch = 0;
+        int seen = 0;
+        cudaGraphExec_t exec = nullptr;
+        std::vector<StageEvt> evts;          // external event-record nodes baked into the graph (timing on)
+        long long launches = 0, conv_launches = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    bool graphs_on = true;
+    bool capturing = false;
+    std::vector<StageEvt>* capture_evts = nullptr;
+    GraphEntry* last_graph = nullptr;        // replayed graph whose timing events still have to be read
+    cudaStream_t graph_stream = nullptr;
+    cudaEvent_t g_ev1 = nullptr, g_ev2 = nullptr;
+
     // host-staged rounds
     ivosw::DeviceBuffer stage_frames, stage_probs, scores_all;
     std::vector<cudaEvent_t> chunk_evts;
