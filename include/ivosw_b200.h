@@ -88,6 +88,24 @@ IVOSW_API int ivosw_brain_load(ivosw_ctx* ctx, const float* params_host, size_t 
 IVOSW_API int ivosw_brain_forward(ivosw_ctx* ctx, const float* state_dev, int N, int T,
                         float* q_dev, int* argmax_dev, void* stream);
 
+/* ---- Double-DQN training step (models/agent.py::Agent.update_agent, :103-166; BASELINE config C4) ----
+ * The policy network is the one loaded with ivosw_brain_load (updated IN PLACE); the target network is
+ * loaded with ivosw_dqn_load_target or copied from the policy with ivosw_dqn_sync_target (the caller
+ * draws np.random.random() < update_rate, agent.py:163-165).  ivosw_dqn_update runs: no-grad policy /
+ * target forwards on new_state, forward + backward on state, element-wise gradient clamp to +-1, Adam
+ * (betas 0.9 / 0.999, eps 1e-8, L2 weight decay in the gradient).  All *_dev arrays are device memory:
+ * state / new_state N x T x 2 fp32, action N int32, rewards N fp32.  loss_host receives the scalar loss
+ * (the call synchronises); grads_dev (nullable, 180 993 floats, blob order) the clamped gradients. */
+IVOSW_API int ivosw_dqn_load_target(ivosw_ctx* ctx, const float* params_host, size_t n_floats);
+IVOSW_API int ivosw_dqn_sync_target(ivosw_ctx* ctx, void* stream);
+IVOSW_API int ivosw_dqn_reset_optimizer(ivosw_ctx* ctx);
+IVOSW_API int ivosw_dqn_update(ivosw_ctx* ctx, const float* state_dev, const float* new_state_dev,
+                     const int* action_dev, const float* reward_step_dev, const float* reward_done_dev,
+                     int N, int T, float gamma, float lr, float weight_decay, float* loss_host,
+                     float* grads_dev, void* stream);
+/* Copies a parameter set (0 = policy, 1 = target) to out_dev (180 993 floats, blob order). */
+IVOSW_API int ivosw_brain_get_params(ivosw_ctx* ctx, int which, float* out_dev, void* stream);
+
 /* ---- quality CNN (models/assessment.py::AssessNet) ---------------------------------------
  * blob_host: fp32, in this order
  *   mean[3], std[3]                                        (Encoder.mean / Encoder.std)

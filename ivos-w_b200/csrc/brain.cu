@@ -38,7 +38,9 @@ __device__ inline float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) brain_inproj_kernel(const float* __restrict__ P,
                                                            const float* __restrict__ state,  // [N][T][2]
-                                                           int T, float* __restrict__ GI) {    // [N][T][512]
+                                                           int T, float* __restrict__ GI,     // [N][T][512]
+                                                           float* __restrict__ A1save,        // nullable [N][T][128]
+                                                           float* __restrict__ Esave) {       // nullable [N][T][128]
     __shared__ float sa[128], se[128];
     const int t = blockIdx.x, n = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(512) brain_inproj_kernel(const float* __restri
         int j = threadIdx.x;
         float v = fmaf(P[P_FC1W + 2 * j + 1], x1, fmaf(P[P_FC1W + 2 * j], x0, 0.f)) + P[P_FC1B + j];
         sa[j] = fmaxf(v, 0.f);
+        if (A1save) A1save[((long long)n * T + t) * 128 + j] = sa[j];
     }
     __syncthreads();
     const float a0 = sa[lane], a1 = sa[lane + 32], a2 = sa[lane + 64], a3 = sa[lane + 96];
@@ -54,7 +57,10 @@ __global__ void __launch_bounds__(512) brain_inproj_kernel(const float* __restri
         const float* w = P + P_FC2W + j * 128;
         float v = w[lane] * a0 + w[lane + 32] * a1 + w[lane + 64] * a2 + w[lane + 96] * a3;
         v = warp_sum(v);
-        if (lane == 0) se[j] = v + P[P_FC2B + j];   // no ReLU after fc2 (agent.py:46)
+        if (lane == 0) {
+            se[j] = v + P[P_FC2B + j];   // no ReLU after fc2 (agent.py:46)
+            if (Esave) Esave[((long long)n * T + t) * 128 + j] = se[j];
+        }
     }
     __syncthreads();
     const float e0 = se[lane], e1 = se[lane + 32], e2 = se[lane + 64], e3 = se[lane + 96];
@@ -81,7 +87,10 @@ __device__ inline float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void __launch_bounds__(512, 1) brain_recurrent_kernel(const float4* __restrict__ whh_pack,
                                                                  const float* __restrict__ GI,  // [N][T][512]
-                                                                 int T, float* __restrict__ Hout) {  // [N][2][T][128]
+                                                                 int T, float* __restrict__ Hout,   // [N][2][T][128]
+                                                                 float* __restrict__ Gsave,         // nullable [N][2][T][512] i,f,g,o
+                                                                 float* __restrict__ Csave,         // nullable [N][2][T][128]
+                                                                 float* __restrict__ HPsave) {      // nullable [N][2][T][128] h before the step
     extern __shared__ __align__(16) float4 sW[];           // [16][512] float4 : k = 64..127
     float* sg = reinterpret_cast<float*>(sW + 16 * 512);   // 512 gate pre-activations
     float* sh = sg + 512;                                  // 128 hidden state
@@ -121,7 +130,14 @@ __global__ void __launch_bounds__(512, 1) brain_recurrent_kernel(const float4* _
         if (j < 128) {
             const float ig = sigmoidf_(sg[j]), fg = sigmoidf_(sg[128 + j]);
             const float gg = tanhf(sg[256 + j]), og = sigmoidf_(sg[384 + j]);
+            const long long st = (((long long)n * 2 + dir) * T + t);
+            if (Gsave) {
+                float* gs = Gsave + st * 512;
+                gs[j] = ig; gs[128 + j] = fg; gs[256 + j] = gg; gs[384 + j] = og;
+                HPsave[st * 128 + j] = sh[j];
+            }
             c = fmaf(fg, c, ig * gg);
+            if (Csave) Csave[st * 128 + j] = c;
             const float h = og * tanhf(c);
             sh[j] = h;
             ho[(long long)t * 128 + j] = h;
@@ -215,21 +231,38 @@ int brain_pack(ivosw_ctx* c) {
     return IVOSW_OK;
 }
 
-int launch_brain(ivosw_ctx* c, const float* state, int N, int T, float* q, int* argmax, cudaStream_t s) {
+// params / whh_pack / d1t select the network (policy or target); the save pointers are for the training step
+int launch_brain_ex(ivosw_ctx* c, const float* params, const float* whh_pack, const float* d1t, const float* state,
+                    int N, int T, float* q, int* argmax, const BrainSaves* sv, cudaStream_t s) {
     int rc;
     if ((rc = ensure(c->brain_gi, sizeof(float) * (size_t)N * T * 512))) return rc;
     if ((rc = ensure(c->brain_h, sizeof(float) * (size_t)N * 2 * T * 128))) return rc;
-    brain_inproj_kernel<<<dim3(T, N), 512, 0, s>>>(c->brain_params, state, T, (float*)c->brain_gi.p);
+    float* hout = sv && sv->H ? sv->H : (float*)c->brain_h.p;
+    brain_inproj_kernel<<<dim3(T, N), 512, 0, s>>>(params, state, T, (float*)c->brain_gi.p, sv ? sv->A1 : nullptr,
+                                                   sv ? sv->E : nullptr);
     IVOSW_CUDA(cudaGetLastError());
     const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
-    brain_recurrent_kernel<<<dim3(2, N), 512, rec_smem, s>>>((const float4*)c->brain_whh_t, (const float*)c->brain_gi.p, T,
-                                                             (float*)c->brain_h.p);
+    brain_recurrent_kernel<<<dim3(2, N), 512, rec_smem, s>>>((const float4*)whh_pack, (const float*)c->brain_gi.p, T, hout,
+                                                             sv ? sv->G : nullptr, sv ? sv->C : nullptr,
+                                                             sv ? sv->HP : nullptr);
     IVOSW_CUDA(cudaGetLastError());
     const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
-    brain_decode_kernel<<<N, 1024, dec_smem, s>>>(c->brain_params, (const float4*)c->brain_d1t, (const float*)c->brain_h.p, T, q,
-                                                  argmax);
+    brain_decode_kernel<<<N, 1024, dec_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
     IVOSW_CUDA(cudaGetLastError());
     c->launches += 3;
+    return IVOSW_OK;
+}
+
+int launch_brain(ivosw_ctx* c, const float* state, int N, int T, float* q, int* argmax, cudaStream_t s) {
+    return launch_brain_ex(c, c->brain_params, c->brain_whh_t, c->brain_d1t, state, N, T, q, argmax, nullptr, s);
+}
+
+// packs W_hh / decoder_fc1 of an arbitrary parameter blob (used for the target network and after each update)
+int brain_pack_into(ivosw_ctx* c, const float* params, float* whh_pack, float* d1t, cudaStream_t s) {
+    brain_pack_whh_kernel<<<(32 * 512 + 255) / 256, 256, 0, s>>>(params + P_WHH, (float4*)whh_pack);
+    brain_pack_d1t_kernel<<<(128 * 256 + 255) / 256, 256, 0, s>>>(params + P_D1W, d1t);
+    c->launches += 2;
+    IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
 }
 

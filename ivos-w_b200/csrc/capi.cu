@@ -287,7 +287,7 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
     return IVOSW_OK;
 }
 
-static int ensure_pinned(ivosw_ctx* c, size_t bytes) {
+int ensure_pinned(ivosw_ctx* c, size_t bytes) {
     if (c->pinned_small_bytes >= bytes) return IVOSW_OK;
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     c->pinned_small = nullptr; c->pinned_small_bytes = 0;
@@ -410,6 +410,12 @@ void ivosw_destroy(ivosw_ctx* c) {
     if (c->brain_params) cudaFree(c->brain_params);
     if (c->brain_whh_t) cudaFree(c->brain_whh_t);
     if (c->brain_d1t) cudaFree(c->brain_d1t);
+    if (c->target_params) cudaFree(c->target_params);
+    if (c->target_whh_t) cudaFree(c->target_whh_t);
+    if (c->target_d1t) cudaFree(c->target_d1t);
+    if (c->adam_m) cudaFree(c->adam_m);
+    if (c->adam_v) cudaFree(c->adam_v);
+    release(c->dqn_ws);
     if (c->stem_w) cudaFree(c->stem_w);
     if (c->stem_scale) cudaFree(c->stem_scale);
     if (c->stem_shift) cudaFree(c->stem_shift);
@@ -478,6 +484,68 @@ int ivosw_brain_forward(ivosw_ctx* c, const float* state_dev, int N, int T, floa
     if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
     IVOSW_CUDA(cudaSetDevice(c->device));
     return launch_brain(c, state_dev, N, T, q_dev, argmax_dev, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------- DQN training step
+int ivosw_dqn_load_target(ivosw_ctx* c, const float* params_host, size_t n_floats) {
+    IVOSW_REQUIRE(c && params_host, "null pointer");
+    IVOSW_REQUIRE(n_floats == IVOSW_BRAIN_NUM_PARAMS, "Brain blob must hold 180993 floats");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(&c->target_params, params_host, n_floats))) return rc;
+    if (!c->target_whh_t) IVOSW_CUDA(cudaMalloc(&c->target_whh_t, sizeof(float4) * 32 * 512));
+    if (!c->target_d1t) IVOSW_CUDA(cudaMalloc(&c->target_d1t, sizeof(float) * 128 * 256));
+    if ((rc = brain_pack_into(c, c->target_params, c->target_whh_t, c->target_d1t, nullptr))) return rc;
+    IVOSW_CUDA(cudaDeviceSynchronize());
+    c->target_loaded = true;
+    return IVOSW_OK;
+}
+
+int ivosw_dqn_sync_target(ivosw_ctx* c, void* stream) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c->target_params) IVOSW_CUDA(cudaMalloc(&c->target_params, sizeof(float) * IVOSW_BRAIN_NUM_PARAMS));
+    if (!c->target_whh_t) IVOSW_CUDA(cudaMalloc(&c->target_whh_t, sizeof(float4) * 32 * 512));
+    if (!c->target_d1t) IVOSW_CUDA(cudaMalloc(&c->target_d1t, sizeof(float) * 128 * 256));
+    IVOSW_CUDA(cudaMemcpyAsync(c->target_params, c->brain_params, sizeof(float) * IVOSW_BRAIN_NUM_PARAMS,
+                               cudaMemcpyDeviceToDevice, s));
+    int rc;
+    if ((rc = brain_pack_into(c, c->target_params, c->target_whh_t, c->target_d1t, s))) return rc;
+    c->target_loaded = true;
+    return IVOSW_OK;
+}
+
+int ivosw_dqn_reset_optimizer(ivosw_ctx* c) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    if (c->adam_m) {
+        IVOSW_CUDA(cudaMemset(c->adam_m, 0, sizeof(float) * IVOSW_BRAIN_NUM_PARAMS));
+        IVOSW_CUDA(cudaMemset(c->adam_v, 0, sizeof(float) * IVOSW_BRAIN_NUM_PARAMS));
+    }
+    c->adam_step = 0;
+    return IVOSW_OK;
+}
+
+int ivosw_dqn_update(ivosw_ctx* c, const float* state_dev, const float* new_state_dev, const int* action_dev,
+                     const float* reward_step_dev, const float* reward_done_dev, int N, int T, float gamma, float lr,
+                     float weight_decay, float* loss_host, float* grads_dev, void* stream) {
+    IVOSW_REQUIRE(c && state_dev && new_state_dev && action_dev && reward_step_dev && reward_done_dev, "null pointer");
+    IVOSW_REQUIRE(N >= 1 && N <= 65535 && T >= 1, "N, T");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return dqn_update(c, state_dev, new_state_dev, action_dev, reward_step_dev, reward_done_dev, N, T, gamma, lr,
+                      weight_decay, loss_host, grads_dev, (cudaStream_t)stream);
+}
+
+int ivosw_brain_get_params(ivosw_ctx* c, int which, float* out_dev, void* stream) {
+    IVOSW_REQUIRE(c && out_dev, "null pointer");
+    const float* src = which == 0 ? c->brain_params : c->target_params;
+    if (!src) { set_error("requested Brain parameter set is not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    IVOSW_CUDA(cudaMemcpyAsync(out_dev, src, sizeof(float) * IVOSW_BRAIN_NUM_PARAMS, cudaMemcpyDeviceToDevice,
+                               (cudaStream_t)stream));
+    return IVOSW_OK;
 }
 
 // --------------------------------------------------------------------------------------- AssessNet

@@ -96,6 +96,15 @@ struct ivosw_ctx {
     float* brain_d1t = nullptr;      // decoder_fc1.weight transposed [256][128]
     float* brain_whh_t = nullptr;    // weight_hh transposed/packed for the recurrent kernel
     ivosw::DeviceBuffer brain_gi, brain_h, brain_state, brain_q, brain_arg;
+    // Double-DQN training step (dqn.cu): target network, Adam moments, saved activations
+    bool target_loaded = false;
+    float* target_params = nullptr;
+    float* target_whh_t = nullptr;
+    float* target_d1t = nullptr;
+    float* adam_m = nullptr;
+    float* adam_v = nullptr;
+    long long adam_step = 0;
+    ivosw::DeviceBuffer dqn_ws;
 
     // AssessNet
     bool assess_loaded = false;
@@ -158,6 +167,7 @@ struct ivosw_ctx {
 namespace ivosw {
 
 int ensure(DeviceBuffer& b, size_t bytes);
+int ensure_pinned(ivosw_ctx* c, size_t bytes);
 // RAII-free stage bracket: stage_begin returns an index (or -1 when timing is off)
 int stage_begin(ivosw_ctx* c, int stage, cudaStream_t s);
 void stage_end(ivosw_ctx* c, int idx, cudaStream_t s);
@@ -188,6 +198,14 @@ int launch_pack_state(ivosw_ctx* c, const double* mq_dev, const double* ann_dev,
 // ---- brain.cu
 int brain_pack(ivosw_ctx* c);
 int launch_brain(ivosw_ctx* c, const float* state, int N, int T, float* q, int* argmax, cudaStream_t s);
+struct BrainSaves { float *A1, *E, *G, *C, *HP, *H; };   // activations kept for the DQN backward pass
+int launch_brain_ex(ivosw_ctx* c, const float* params, const float* whh_pack, const float* d1t, const float* state,
+                    int N, int T, float* q, int* argmax, const BrainSaves* sv, cudaStream_t s);
+int brain_pack_into(ivosw_ctx* c, const float* params, float* whh_pack, float* d1t, cudaStream_t s);
+// ---- dqn.cu
+int dqn_update(ivosw_ctx* c, const float* state, const float* new_state, const int* action, const float* reward_step,
+               const float* reward_done, int N, int T, float gamma, float lr, float weight_decay, float* loss_host,
+               float* grads_out_dev, cudaStream_t s);
 // ---- manet_tail.cu
 int launch_manet_tail(ivosw_ctx* c, const float* logits, int T, int C, int h, int w, int H, int W, float* masks,
                       float* all_p, cudaStream_t s);

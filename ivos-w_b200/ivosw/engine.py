@@ -121,6 +121,48 @@ class Engine:
         check(lib.ivosw_brain_forward(self._h, _ptr(state), N, T, _ptr(q), _ptr(am), _stream(self.device)))
         return (q, am) if want_argmax else q
 
+    # ------------------------------------------------------------------ DQN step (models/agent.py:103-166)
+    def load_target(self, sd):
+        blob = pack_brain(sd)
+        check(lib.ivosw_dqn_load_target(self._h, _np_ptr(blob), blob.size))
+
+    def sync_target(self):
+        check(lib.ivosw_dqn_sync_target(self._h, _stream(self.device)))
+
+    def reset_optimizer(self):
+        check(lib.ivosw_dqn_reset_optimizer(self._h))
+
+    def dqn_update(self, state, new_state, action, reward_step, reward_done, gamma=0.95, lr=5e-6, weight_decay=5e-4,
+                   want_grads=False):
+        """One Agent.update_agent step on CUDA tensors: state/new_state N x T x 2, action N, rewards N.
+        The policy parameters inside the library are updated in place.  Returns loss [, clamped grads]."""
+        state, new_state = self._dev32(state), self._dev32(new_state)
+        N, T, _ = state.shape
+        action = action.to(self.device, torch.int32).contiguous().view(-1)
+        rs = self._dev32(reward_step).view(-1)
+        rd = self._dev32(reward_done).view(-1)
+        grads = torch.empty((BRAIN_NUM_PARAMS,), device=self.device, dtype=torch.float32) if want_grads else None
+        loss = C.c_float(0.0)
+        check(lib.ivosw_dqn_update(self._h, _ptr(state), _ptr(new_state), _ptr(action), _ptr(rs), _ptr(rd), N, T,
+                                   gamma, lr, weight_decay, C.byref(loss), _ptr(grads), _stream(self.device)))
+        return (float(loss.value), grads) if want_grads else float(loss.value)
+
+    def brain_params(self, which="policy"):
+        """Flat parameter blob (blob order) of the policy / target network currently inside the library."""
+        out = torch.empty((BRAIN_NUM_PARAMS,), device=self.device, dtype=torch.float32)
+        check(lib.ivosw_brain_get_params(self._h, 0 if which == "policy" else 1, _ptr(out), _stream(self.device)))
+        return out
+
+    @staticmethod
+    def unpack_brain(flat):
+        """flat blob -> dict of tensors with the reference's state-dict keys."""
+        sd, o = {}, 0
+        for key, shape in arch.BRAIN_PARAMS:
+            n = int(np.prod(shape))
+            sd[key] = flat[o:o + n].view(shape)
+            o += n
+        return sd
+
     # ------------------------------------------------------------------ AssessNet (models/assessment.py:164)
     def assess_forward(self, tf, tp, want_boxes=False):
         """tf: B x 3 x H x W, tp: B x H x W (CUDA fp32; tp may be a strided slice such as

@@ -212,6 +212,66 @@ def golden_manet_tail():
     print("manet_tail.npz", masks.shape, all_P.shape)
 
 
+def synth_dqn_batch(seed, N=256, T=25):
+    """BASELINE config C4 inputs: IoU ~ U[0.3, 0.95], annotated counts = histogram of
+    k in [1, 5] random frames, action ~ U{0..T-1}, reward_step in {-1, +1}, reward_done ~ N(0, 1)."""
+    rng = np.random.default_rng(seed)
+    def ann():
+        a = np.zeros((N, T))
+        for n in range(N):
+            for i in rng.integers(0, T, size=rng.integers(1, 6)):
+                a[n, i] += 1
+        return a
+    a0 = ann()
+    a1 = a0.copy()
+    act = rng.integers(0, T, size=N)
+    a1[np.arange(N), act] += 1
+    return {
+        "old_state_iou": torch.from_numpy(rng.uniform(0.3, 0.95, (N, T))),
+        "new_state_iou": torch.from_numpy(rng.uniform(0.3, 0.95, (N, T))),
+        "annotated_frames": torch.from_numpy(a0), "next_annotated_frames": torch.from_numpy(a1),
+        "action": torch.from_numpy(act), "reward_step": torch.from_numpy(rng.choice([-1.0, 1.0], N)),
+        "reward_done": torch.from_numpy(rng.standard_normal(N)), "done": torch.zeros(N),
+    }
+
+
+def golden_dqn(ref_agent):
+    """Two consecutive Agent.update_agent steps of the reference on CPU (target net = a second seed)."""
+    out = {}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        cfg = agent_cfg()
+        cfg.phase = "train"
+        agent = ref_agent.Agent("cpu", cfg)
+        agent.policy_net.load_state_dict(synth.brain_state_dict(0))
+        agent.target_net.load_state_dict(synth.brain_state_dict(1))
+        agent.policy_net.to(dt); agent.target_net.to(dt)
+        agent.optimizer = torch.optim.Adam(agent.policy_net.parameters(), lr=cfg.agent.lr,
+                                           weight_decay=cfg.agent.weight_decay)
+        np.random.seed(12345)       # the stochastic target sync must not fire (update_rate 0.05)
+        for step in range(2):
+            batch = synth_dqn_batch(100 + step, 64 if dt == torch.float64 else 256, 25)
+            if dt == torch.float64:
+                # the reference casts inputs with .float(); keep the arbiter in fp64 by pre-casting its tensors
+                orig_float = torch.Tensor.float
+                torch.Tensor.float = lambda self, *a, **k: self.double() if self.is_floating_point() else orig_float(self).double()
+            before = np.random.get_state()[2]
+            loss = agent.update_agent(batch)
+            if dt == torch.float64:
+                torch.Tensor.float = orig_float
+            out["%s_loss%d" % (tag, step)] = np.float64(loss)
+            if tag == "f32":    # fixtures kept small: full gradients of step 0, every 8th value afterwards
+                for k, v in agent.policy_net.named_parameters():
+                    g = v.grad.detach().numpy().reshape(-1)
+                    out["grad%d_%s" % (step, k)] = g.copy() if step == 0 else g[::8].copy()
+                    if step == 1:
+                        out["param_final_%s" % k] = v.detach().numpy().reshape(-1)[::8].copy()
+        tgt_same = all(torch.equal(a, b.to(dt)) for a, b in zip(agent.target_net.state_dict().values(),
+                                                                 synth.brain_state_dict(1).values()))
+        assert tgt_same, "target sync fired; pick another numpy seed"
+    np.savez_compressed(os.path.join(HERE, "dqn_step.npz"), **out)
+    print("dqn_step.npz: loss f32", out["f32_loss0"], out["f32_loss1"], "f64", out["f64_loss0"], out["f64_loss1"])
+
+
 if __name__ == "__main__":
     ref_assess, ref_agent, ref_glue = load_reference()
     with torch.no_grad():
@@ -222,3 +282,4 @@ if __name__ == "__main__":
         golden_round("round_single", 2, 1, 160, 288, 3, "manet", ref_assess, ref_agent, ref_glue)
         golden_round("round_t16", 4, 16, 128, 224, 2, "manet", ref_assess, ref_agent, ref_glue)
         golden_manet_tail()
+    golden_dqn(ref_agent)

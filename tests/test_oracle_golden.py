@@ -101,3 +101,40 @@ def test_manet_tail(golden_dir):
     masks, all_P = manet_tail_ref.manet_tail(g["logits"], H, W)
     np.testing.assert_array_equal(masks.numpy().astype(np.uint8), g["masks"])
     np.testing.assert_allclose(all_P.numpy(), g["all_P"], atol=1e-7)
+
+
+def _dqn_batch(seed, N=256, T=25):
+    """Same generator as tests/golden/make_golden.py::synth_dqn_batch."""
+    rng = np.random.default_rng(seed)
+
+    def ann():
+        a = np.zeros((N, T))
+        for n in range(N):
+            for i in rng.integers(0, T, size=rng.integers(1, 6)):
+                a[n, i] += 1
+        return a
+    a0 = ann()
+    a1 = a0.copy()
+    act = rng.integers(0, T, size=N)
+    a1[np.arange(N), act] += 1
+    old_iou = rng.uniform(0.3, 0.95, (N, T)); new_iou = rng.uniform(0.3, 0.95, (N, T))
+    rs = rng.choice([-1.0, 1.0], N); rd = rng.standard_normal(N)
+    return (np.stack([old_iou, a0], 2), np.stack([new_iou, a1], 2), act, rs, rd)
+
+
+def test_dqn_step_matches_reference(golden_dir):
+    from oracle import dqn_ref
+    g = _load(golden_dir, "dqn_step")
+    st = dqn_ref.DqnState(synth.brain_state_dict(0), synth.brain_state_dict(1))
+    for step in range(2):
+        s, ns, act, rs, rd = _dqn_batch(100 + step)
+        loss, grads = dqn_ref.update_agent(st, torch.from_numpy(s).float(), torch.from_numpy(ns).float(),
+                                           torch.from_numpy(act), torch.from_numpy(rs).float(), torch.from_numpy(rd).float())
+        assert abs(loss - float(g["f32_loss%d" % step])) < 1e-7
+        for k, gr in grads.items():
+            ref = g["grad%d_%s" % (step, k)]
+            mine = gr.numpy().reshape(-1)
+            mine = mine if step == 0 else mine[::8]
+            np.testing.assert_allclose(mine, ref, atol=1e-7, rtol=1e-4, err_msg=k)
+    for k, v in st.p.items():
+        np.testing.assert_allclose(v.detach().numpy().reshape(-1)[::8], g["param_final_" + k], atol=2e-7, err_msg=k)
