@@ -102,7 +102,12 @@ IVOSW_API int ivosw_dqn_reset_optimizer(ivosw_ctx* ctx);
 IVOSW_API int ivosw_dqn_update(ivosw_ctx* ctx, const float* state_dev, const float* new_state_dev,
                      const int* action_dev, const float* reward_step_dev, const float* reward_done_dev,
                      int N, int T, float gamma, float lr, float weight_decay, float* loss_host,
-                     float* grads_dev, void* stream);
+                     float* grads_dev, int apply_update, void* stream);
+/* Data-parallel form: call ivosw_dqn_update(apply_update = 0) on every rank's slice of the batch (grads_dev
+ * then receives the RAW gradient of that slice's mean loss), average grads_dev across ranks (one NCCL
+ * all-reduce of 724 KB), then ivosw_dqn_apply clamps to +-1 and takes the Adam step — the same arithmetic
+ * as one full-batch update.  grads_dev is overwritten with the clamped gradient. */
+IVOSW_API int ivosw_dqn_apply(ivosw_ctx* ctx, float* grads_dev, float lr, float weight_decay, void* stream);
 /* Copies a parameter set (0 = policy, 1 = target) to out_dev (180 993 floats, blob order). */
 IVOSW_API int ivosw_brain_get_params(ivosw_ctx* ctx, int which, float* out_dev, void* stream);
 

@@ -530,12 +530,20 @@ int ivosw_dqn_reset_optimizer(ivosw_ctx* c) {
 
 int ivosw_dqn_update(ivosw_ctx* c, const float* state_dev, const float* new_state_dev, const int* action_dev,
                      const float* reward_step_dev, const float* reward_done_dev, int N, int T, float gamma, float lr,
-                     float weight_decay, float* loss_host, float* grads_dev, void* stream) {
+                     float weight_decay, float* loss_host, float* grads_dev, int apply_update, void* stream) {
     IVOSW_REQUIRE(c && state_dev && new_state_dev && action_dev && reward_step_dev && reward_done_dev, "null pointer");
     IVOSW_REQUIRE(N >= 1 && N <= 65535 && T >= 1, "N, T");
+    IVOSW_REQUIRE(apply_update || grads_dev, "grads_dev is required when the optimiser step is deferred");
     IVOSW_CUDA(cudaSetDevice(c->device));
     return dqn_update(c, state_dev, new_state_dev, action_dev, reward_step_dev, reward_done_dev, N, T, gamma, lr,
-                      weight_decay, loss_host, grads_dev, (cudaStream_t)stream);
+                      weight_decay, loss_host, grads_dev, apply_update != 0, (cudaStream_t)stream);
+}
+
+int ivosw_dqn_apply(ivosw_ctx* c, float* grads_dev, float lr, float weight_decay, void* stream) {
+    IVOSW_REQUIRE(c && grads_dev, "null pointer");
+    if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return dqn_apply(c, grads_dev, lr, weight_decay, (cudaStream_t)stream);
 }
 
 int ivosw_brain_get_params(ivosw_ctx* c, int which, float* out_dev, void* stream) {

@@ -245,9 +245,30 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
 
 }  // namespace
 
+// clamp + Adam(weight decay) on the policy parameters, in place; `grad` is overwritten with the clamped gradient
+int dqn_apply(ivosw_ctx* c, float* grad, float lr, float weight_decay, cudaStream_t s) {
+    int rc;
+    if (!c->adam_m) {
+        IVOSW_CUDA(cudaMalloc(&c->adam_m, sizeof(float) * NPARAM));
+        IVOSW_CUDA(cudaMalloc(&c->adam_v, sizeof(float) * NPARAM));
+        IVOSW_CUDA(cudaMemsetAsync(c->adam_m, 0, sizeof(float) * NPARAM, s));
+        IVOSW_CUDA(cudaMemsetAsync(c->adam_v, 0, sizeof(float) * NPARAM, s));
+        c->adam_step = 0;
+    }
+    c->adam_step += 1;
+    const float bc1 = (float)(1.0 - pow(0.9, (double)c->adam_step));            // torch computes these in double
+    const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)c->adam_step));
+    adam_kernel<<<(NPARAM + 255) / 256, 256, 0, s>>>(c->brain_params, grad, c->adam_m, c->adam_v, NPARAM, lr, weight_decay,
+                                                     bc1, bc2s);
+    IVOSW_CUDA(cudaGetLastError());
+    c->launches += 1;
+    if ((rc = brain_pack_into(c, c->brain_params, c->brain_whh_t, c->brain_d1t, s))) return rc;   // inference copies
+    return IVOSW_OK;
+}
+
 int dqn_update(ivosw_ctx* c, const float* state, const float* new_state, const int* action, const float* reward_step,
                const float* reward_done, int N, int T, float gamma, float lr, float weight_decay, float* loss_host,
-               float* grads_out_dev, cudaStream_t s) {
+               float* grads_out_dev, bool apply, cudaStream_t s) {
     int rc;
     if (!c->brain_loaded || !c->target_loaded) { set_error("policy / target Brain weights not loaded"); return IVOSW_ERR_STATE; }
     const size_t NT = (size_t)N * T;
@@ -263,13 +284,6 @@ int dqn_update(ivosw_ctx* c, const float* state, const float* new_state, const i
     if ((rc = ensure(c->dqn_ws, off * sizeof(float)))) return rc;
     float* W = (float*)c->dqn_ws.p;
     float* grad = W + o_grad;
-    if (!c->adam_m) {
-        IVOSW_CUDA(cudaMalloc(&c->adam_m, sizeof(float) * NPARAM));
-        IVOSW_CUDA(cudaMalloc(&c->adam_v, sizeof(float) * NPARAM));
-        IVOSW_CUDA(cudaMemsetAsync(c->adam_m, 0, sizeof(float) * NPARAM, s));
-        IVOSW_CUDA(cudaMemsetAsync(c->adam_v, 0, sizeof(float) * NPARAM, s));
-        c->adam_step = 0;
-    }
     const float* Pp = c->brain_params;
     // ---- no-grad forwards on the new state (policy -> a*, target -> Q_next)
     if ((rc = launch_brain_ex(c, Pp, c->brain_whh_t, c->brain_d1t, new_state, N, T, W + o_qpn, (int*)(W + o_astar), nullptr, s)))
@@ -311,17 +325,13 @@ int dqn_update(ivosw_ctx* c, const float* state, const float* new_state, const i
     colsum_kernel<<<1, 128, 0, s>>>(W + o_da1, R1, 128, grad + P_FC1B);
     IVOSW_CUDA(cudaGetLastError());
     c->launches += 5;
-    // ---- clamp + Adam(weight decay) on the policy parameters, in place
-    c->adam_step += 1;
-    const float bc1 = (float)(1.0 - pow(0.9, (double)c->adam_step));            // torch computes these in double
-    const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)c->adam_step));
-    adam_kernel<<<(NPARAM + 255) / 256, 256, 0, s>>>(c->brain_params, grad, c->adam_m, c->adam_v, NPARAM, lr, weight_decay,
-                                                     bc1, bc2s);
-    IVOSW_CUDA(cudaGetLastError());
-    c->launches += 1;
-    if (grads_out_dev)
-        IVOSW_CUDA(cudaMemcpyAsync(grads_out_dev, grad, sizeof(float) * NPARAM, cudaMemcpyDeviceToDevice, s));
-    if ((rc = brain_pack_into(c, c->brain_params, c->brain_whh_t, c->brain_d1t, s))) return rc;   // inference copies
+    if (grads_out_dev)   // raw (unclamped) gradients when the optimiser step is deferred, clamped ones otherwise
+        if (!apply) IVOSW_CUDA(cudaMemcpyAsync(grads_out_dev, grad, sizeof(float) * NPARAM, cudaMemcpyDeviceToDevice, s));
+    if (apply) {
+        if ((rc = dqn_apply(c, grad, lr, weight_decay, s))) return rc;
+        if (grads_out_dev)
+            IVOSW_CUDA(cudaMemcpyAsync(grads_out_dev, grad, sizeof(float) * NPARAM, cudaMemcpyDeviceToDevice, s));
+    }
     if ((rc = ensure_pinned(c, 64))) return rc;
     IVOSW_CUDA(cudaMemcpyAsync(c->pinned_small, W + o_loss, sizeof(float), cudaMemcpyDeviceToHost, s));
     IVOSW_CUDA(cudaStreamSynchronize(s));

@@ -205,7 +205,8 @@ int brain_pack_into(ivosw_ctx* c, const float* params, float* whh_pack, float* d
 // ---- dqn.cu
 int dqn_update(ivosw_ctx* c, const float* state, const float* new_state, const int* action, const float* reward_step,
                const float* reward_done, int N, int T, float gamma, float lr, float weight_decay, float* loss_host,
-               float* grads_out_dev, cudaStream_t s);
+               float* grads_out_dev, bool apply, cudaStream_t s);
+int dqn_apply(ivosw_ctx* c, float* grad, float lr, float weight_decay, cudaStream_t s);
 // ---- manet_tail.cu
 int launch_manet_tail(ivosw_ctx* c, const float* logits, int T, int C, int h, int w, int H, int W, float* masks,
                       float* all_p, cudaStream_t s);

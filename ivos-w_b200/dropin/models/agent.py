@@ -112,10 +112,53 @@ class Agent(nn.Module):
             action_idx = np.array(range(state.shape[0]))
             return random.choice(action_idx)
 
+    def _sync_target(self, engine):
+        sd = self.target_net.state_dict()
+        stamp = tuple((sd[k].data_ptr(), sd[k]._version) for k, _ in arch.BRAIN_PARAMS) + (id(engine),)
+        if stamp != getattr(self, "_target_uploaded", None):
+            engine.load_target(sd)
+            self._target_uploaded = stamp
+
     def update_agent(self, sample):
-        raise NotImplementedError(
-            "Agent.update_agent (Double-DQN training step, agent.py:103-166) is a 'next' row of the scope "
-            "table (SURVEY.md §8(f) rank 2) and is not built yet; the inference path never calls it.")
+        """Double-DQN step (agent.py:103-166) as one device-side update in the CUDA library: no-grad target
+        computation, forward/backward of the bi-LSTM Q-network, element-wise gradient clamp, Adam with L2 weight
+        decay.  The Adam moments live inside the library (one training agent per device); the updated
+        parameters are copied back into ``policy_net`` so checkpoints keep working."""
+        if sample is None:
+            print('no input')
+            return
+        N = sample['action'].shape[0]
+
+        def col(k):
+            return sample[k].float().view(N, -1).to(self.device)
+
+        state = torch.stack([col('old_state_iou'), col('annotated_frames')], 2)
+        new_state = torch.stack([col('new_state_iou'), col('next_annotated_frames')], 2)
+        engine = get_engine(self.device)
+        self.policy_net._sync(engine)
+        self._sync_target(engine)
+        group = self.optimizer.param_groups[0]
+        loss = engine.dqn_update(state, new_state, sample['action'].view(N), col('reward_step').view(N),
+                                 col('reward_done').view(N), gamma=float(self.GAMMA), lr=float(group['lr']),
+                                 weight_decay=float(group['weight_decay']))
+        new_sd = engine.unpack_brain(engine.brain_params("policy"))
+        with torch.no_grad():
+            for k, p in self.policy_net.named_parameters():
+                p.copy_(new_sd[k])
+        sd = self.policy_net.state_dict()     # the library already holds these values: refresh the stamp, no re-upload
+        self.policy_net._uploaded = tuple((sd[k].data_ptr(), sd[k]._version) for k, _ in arch.BRAIN_PARAMS) + (id(engine),)
+        self._update_avg_loss(loss)
+        if np.random.random() < self.update_rate:                      # stochastic hard target sync (:163-165)
+            print("target_net updated!")
+            self.target_net.load_state_dict(self.policy_net.state_dict())
+        return loss
+
+    def _update_avg_loss(self, loss):
+        if len(self.loss) < self.loss_capacity:
+            self.loss.append(None)
+        self.loss[self.loss_position] = float(loss)
+        self.loss_position = (self.loss_position + 1) % self.loss_capacity
+        self.loss_avg = sum(self.loss) / len(self.loss)
 
     def set_train(self):
         self.policy_net.train()

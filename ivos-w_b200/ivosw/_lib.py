@@ -31,7 +31,8 @@ SYMBOLS = {
     "ivosw_dqn_sync_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ivosw_dqn_reset_optimizer": (C.c_int, [C.c_void_p]),
     "ivosw_dqn_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                   C.c_int, C.c_float, C.c_float, C.c_float, _c_f, C.c_void_p, C.c_void_p]),
+                                   C.c_int, C.c_float, C.c_float, C.c_float, _c_f, C.c_void_p, C.c_int, C.c_void_p]),
+    "ivosw_dqn_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "ivosw_brain_get_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ivosw_assess_blob_floats": (C.c_size_t, []),
     "ivosw_assess_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -61,3 +61,22 @@ def host_gather_round(local_mq, T, annotated_counts, action_fn, group=None):
         out[:per] = send
     mq = out[:T].numpy()
     return action_fn(mq, annotated_counts), mq
+
+
+def dqn_update_data_parallel(engine, state, new_state, action, reward_step, reward_done, gamma=0.95, lr=5e-6,
+                             weight_decay=5e-4, group=None):
+    """BASELINE config C4, data-parallel: every rank passes ITS slice of the replay batch; raw gradients of
+    the slice-mean losses are averaged with ONE all-reduce (724 KB), then every rank clamps and takes the
+    identical Adam step.  Equal slice sizes reproduce the single-GPU full-batch update (agent.py:103-166).
+    Returns the global mean loss."""
+    loss, grads = engine.dqn_update(state, new_state, action, reward_step, reward_done, gamma=gamma, lr=lr,
+                                    weight_decay=weight_decay, apply=False)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        lt = torch.tensor([loss], device=engine.device, dtype=torch.float32)
+        dist.all_reduce(grads, group=group)
+        dist.all_reduce(lt, group=group)
+        grads /= world
+        loss = float(lt.item()) / world
+    engine.dqn_apply(grads, lr=lr, weight_decay=weight_decay)
+    return loss

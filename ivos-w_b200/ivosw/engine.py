@@ -133,7 +133,7 @@ class Engine:
         check(lib.ivosw_dqn_reset_optimizer(self._h))
 
     def dqn_update(self, state, new_state, action, reward_step, reward_done, gamma=0.95, lr=5e-6, weight_decay=5e-4,
-                   want_grads=False):
+                   want_grads=False, apply=True):
         """One Agent.update_agent step on CUDA tensors: state/new_state N x T x 2, action N, rewards N.
         The policy parameters inside the library are updated in place.  Returns loss [, clamped grads]."""
         state, new_state = self._dev32(state), self._dev32(new_state)
@@ -141,11 +141,18 @@ class Engine:
         action = action.to(self.device, torch.int32).contiguous().view(-1)
         rs = self._dev32(reward_step).view(-1)
         rd = self._dev32(reward_done).view(-1)
+        want_grads = want_grads or not apply
         grads = torch.empty((BRAIN_NUM_PARAMS,), device=self.device, dtype=torch.float32) if want_grads else None
         loss = C.c_float(0.0)
         check(lib.ivosw_dqn_update(self._h, _ptr(state), _ptr(new_state), _ptr(action), _ptr(rs), _ptr(rd), N, T,
-                                   gamma, lr, weight_decay, C.byref(loss), _ptr(grads), _stream(self.device)))
+                                   gamma, lr, weight_decay, C.byref(loss), _ptr(grads), 1 if apply else 0,
+                                   _stream(self.device)))
         return (float(loss.value), grads) if want_grads else float(loss.value)
+
+    def dqn_apply(self, grads, lr=5e-6, weight_decay=5e-4):
+        """Clamp + Adam step on (all-reduced) raw gradients; ``grads`` is overwritten with the clamped values."""
+        assert grads.is_cuda and grads.dtype == torch.float32 and grads.numel() == BRAIN_NUM_PARAMS
+        check(lib.ivosw_dqn_apply(self._h, _ptr(grads), lr, weight_decay, _stream(self.device)))
 
     def brain_params(self, which="policy"):
         """Flat parameter blob (blob order) of the policy / target network currently inside the library."""

@@ -91,3 +91,62 @@ def test_dqn_vs_oracle_other_shapes():
         for k, _ in arch.BRAIN_PARAMS:
             np.testing.assert_allclose(gd[k].cpu().numpy(), ref_g[k].numpy(), atol=3e-6, rtol=3e-3, err_msg=k)
     eng.close()
+
+
+def test_dqn_data_parallel_arithmetic():
+    """Two engines standing in for two ranks: raw gradients of the half batches, averaged, then clamp + Adam,
+    must reproduce the single full-batch update."""
+    from ivosw.engine import Engine
+    full, r0, r1 = Engine(0), Engine(0), Engine(0)
+    for e in (full, r0, r1):
+        e.load_brain(synth.brain_state_dict(0)); e.load_target(synth.brain_state_dict(1)); e.reset_optimizer()
+    s, ns, act, rs, rd = _dqn_batch(100)
+    t = lambda a, sl: torch.from_numpy(a[sl]).float().cuda()
+    loss_full, g_full = full.dqn_update(t(s, slice(None)), t(ns, slice(None)), torch.from_numpy(act).cuda(), t(rs, slice(None)),
+                                        t(rd, slice(None)), want_grads=True)
+    halves = []
+    for e, sl in ((r0, slice(0, 128)), (r1, slice(128, 256))):
+        halves.append(e.dqn_update(t(s, sl), t(ns, sl), torch.from_numpy(act[sl]).cuda(), t(rs, sl), t(rd, sl), apply=False))
+    loss_dp = 0.5 * (halves[0][0] + halves[1][0])
+    g = 0.5 * (halves[0][1] + halves[1][1])
+    assert abs(loss_dp - loss_full) <= 2e-6 * abs(loss_full)
+    for e in (r0, r1):
+        gg = g.clone()
+        e.dqn_apply(gg)
+        np.testing.assert_allclose(gg.cpu().numpy(), g_full.cpu().numpy(), atol=1e-6, rtol=1e-3)
+        np.testing.assert_allclose(e.brain_params().cpu().numpy(), full.brain_params().cpu().numpy(), atol=1e-6)
+    for e in (full, r0, r1):
+        e.close()
+
+
+def test_dropin_agent_update_matches_reference(golden_dir):
+    """The drop-in Agent.update_agent (same signature / sample dict as agent.py:103) against the reference fixture."""
+    import sys
+    from types import SimpleNamespace
+    REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = os.path.join(REPO, "ivos-w_b200", "dropin")
+    for m in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")]:
+        del sys.modules[m]
+    sys.path.insert(0, p)
+    import models.agent as A
+    sys.path.remove(p)
+    g = np.load(os.path.join(golden_dir, "dqn_step.npz"))
+    cfg = SimpleNamespace(phase="train", agent=SimpleNamespace(memory_size=10, gamma=0.95, eps_start=0.7, eps_end=0.25,
+                          eps_decay=500, update_rate=0.05, lr=5e-6, weight_decay=5e-4), data=SimpleNamespace(subset="train"))
+    agent = A.Agent("cuda:0", cfg)
+    agent.policy_net.load_state_dict(synth.brain_state_dict(0))
+    agent.target_net.load_state_dict(synth.brain_state_dict(1))
+    from ivosw.engine import get_engine
+    get_engine("cuda:0").reset_optimizer()
+    np.random.seed(12345)
+    for step in range(2):
+        s, ns, act, rs, rd = _dqn_batch(100 + step)
+        sample = {"old_state_iou": torch.from_numpy(s[..., 0]), "annotated_frames": torch.from_numpy(s[..., 1]),
+                  "new_state_iou": torch.from_numpy(ns[..., 0]), "next_annotated_frames": torch.from_numpy(ns[..., 1]),
+                  "action": torch.from_numpy(act), "reward_step": torch.from_numpy(rs), "reward_done": torch.from_numpy(rd),
+                  "done": torch.zeros(len(act))}
+        loss = agent.update_agent(sample)
+        assert abs(loss - float(g["f32_loss%d" % step])) <= 2e-6 * abs(loss)
+    for k, v in agent.policy_net.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy().reshape(-1)[::8], g["param_final_" + k], atol=2e-6, err_msg=k)
+    assert abs(agent.get_avg_loss() - 0.5 * (float(g["f32_loss0"]) + float(g["f32_loss1"]))) < 1e-6
