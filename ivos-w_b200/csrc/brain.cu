@@ -4,15 +4,23 @@
 //   brain_inproj_kernel     all frames in parallel:  e_t = fc2(relu(fc1(x_t)));  gi_t = W_ih e_t.
 //                           The same LSTMCell serves both directions (agent.py:48-49), so gi_t is
 //                           computed once and shared by the forward and backward chains.
-//   brain_recurrent_kernel  one CTA per (direction, batch row): the T-step dependency chain
-//                           gates = gi_t + W_hh h_{t-1} with W_hh resident on chip (half in
-//                           registers, half in shared memory), zero initial state, gate order i,f,g,o,
-//                           no bias (LSTMCell(..., bias=False), agent.py:24-25).
+//   brain_recurrent_cluster_kernel
+//                           the T-step dependency chain gates = gi_t + W_hh h_{t-1} (zero initial state,
+//                           gate order i,f,g,o, no bias: LSTMCell(..., bias=False), agent.py:24-25) on a
+//                           cluster of 4 CTAs per (direction, batch row): W_hh (256 KB) lives entirely in
+//                           the clusters' registers (each CTA owns 32 hidden units = 128 gate rows, a thread
+//                           holds 32 weights), h is exchanged through distributed shared memory once per
+//                           step.  brain_recurrent_kernel (one CTA, W_hh half in registers / half in smem)
+//                           is the variant that also saves activations for the training step.
 //   brain_decode_kernel     Q_t = fc_d2(relu(fc_d1(relu([h_fw_t ; h_bw_t]))))  (agent.py:55-60) and
 //                           argmax over t, first maximum wins (numpy semantics).
 //
 // Latency-bound (2T dependent steps); weights are 724 KB and stay in L2 / on chip.
+#include <cooperative_groups.h>
+
 #include "ivosw_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace ivosw {
 
@@ -216,6 +224,9 @@ __global__ void __launch_bounds__(1024, 1) brain_decode_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+__global__ void brain_decode8_kernel(const float* __restrict__ P, const float4* __restrict__ d1t,
+                                     const float* __restrict__ Hout, int T, float* __restrict__ Q, int* __restrict__ argmax);
+
 int brain_pack(ivosw_ctx* c) {
     if (!c->brain_whh_t) IVOSW_CUDA(cudaMalloc(&c->brain_whh_t, sizeof(float4) * 32 * 512));
     brain_pack_whh_kernel<<<(32 * 512 + 255) / 256, 256>>>(c->brain_params + P_WHH, (float4*)c->brain_whh_t);
@@ -227,8 +238,153 @@ int brain_pack(ivosw_ctx* c) {
     const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
     IVOSW_CUDA(cudaFuncSetAttribute(brain_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_smem));
     IVOSW_CUDA(cudaFuncSetAttribute(brain_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+    IVOSW_CUDA(cudaFuncSetAttribute(brain_decode8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (256 * 128 + 8 * 256 * 8 + 8 * 4 * 8) * 4));
     IVOSW_CUDA(cudaDeviceSynchronize());
     return IVOSW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cluster variant of the recurrence (inference path).  grid = (4, 2 directions, N), cluster = 4 CTAs.
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(512, 1)
+brain_recurrent_cluster_kernel(const float* __restrict__ P, const float* __restrict__ GI,   // [N][T][512]
+                               int T, float* __restrict__ Hout) {                            // [N][2][T][128]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();          // owns hidden units [32r, 32r + 32)
+    const int dir = blockIdx.y, n = blockIdx.z;
+    __shared__ __align__(16) float sh[2][128];        // hidden state, double-buffered across steps
+    __shared__ float spart[4][4][32];                 // [k quarter][gate][unit]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp >> 2, kq = warp & 3;           // this warp: gate g, k in [32kq, 32kq + 32), unit = lane
+    float4 w[8];
+    {
+        const float4* wrow = reinterpret_cast<const float4*>(P + P_WHH + (size_t)(g * 128 + 32 * r + lane) * 128 + 32 * kq);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __ldg(wrow + i);
+    }
+    if (threadIdx.x < 128) { sh[0][threadIdx.x] = 0.f; sh[1][threadIdx.x] = 0.f; }
+    float c = 0.f;
+    const float* gi = GI + (long long)n * T * 512 + 32 * r + lane;
+    float* ho = Hout + ((long long)n * 2 + dir) * T * 128 + 32 * r + lane;
+    float* peer[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) peer[rr] = cluster.map_shared_rank(&sh[0][0], rr);
+    int t = dir == 0 ? 0 : T - 1;
+    float gin[4] = {0.f, 0.f, 0.f, 0.f};
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gin[q] = gi[(long long)t * 512 + q * 128];
+    }
+    cluster.sync();
+    for (int s = 0; s < T; ++s) {
+        const int tn = dir == 0 ? t + 1 : t - 1;
+        float gnext[4] = {0.f, 0.f, 0.f, 0.f};
+        if (warp == 0 && s + 1 < T) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gnext[q] = gi[(long long)tn * 512 + q * 128];   // prefetch across the step
+        }
+        const float4* h4 = reinterpret_cast<const float4*>(&sh[s & 1][32 * kq]);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 h = h4[i];
+            a0 = fmaf(w[i].x, h.x, a0); a1 = fmaf(w[i].y, h.y, a1);
+            a2 = fmaf(w[i].z, h.z, a2); a3 = fmaf(w[i].w, h.w, a3);
+        }
+        spart[kq][g][lane] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (warp == 0) {
+            float pre[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                pre[q] = gin[q] + ((spart[0][q][lane] + spart[1][q][lane]) + (spart[2][q][lane] + spart[3][q][lane]));
+            const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]), og = sigmoidf_(pre[3]);
+            c = fmaf(fg, c, ig * gg);
+            const float h = og * tanhf(c);
+            ho[(long long)t * 128] = h;
+            const int slot = ((s + 1) & 1) * 128 + 32 * r + lane;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) peer[rr][slot] = h;      // distributed shared memory broadcast
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gin[q] = gnext[q];
+        }
+        cluster.sync();                                             // h visible cluster-wide; spart reusable
+        t = tn;
+    }
+}
+
+// Decoder + argmax, register-blocked over 8 frames per thread: 1024 threads = 8 groups x 128 decoder units,
+// a group handles 8 frames at a time so every weight read from shared memory feeds 8 FMAs.
+__global__ void __launch_bounds__(1024, 1) brain_decode8_kernel(const float* __restrict__ P,
+                                                                const float4* __restrict__ d1t,
+                                                                const float* __restrict__ Hout,  // [N][2][T][128]
+                                                                int T, float* __restrict__ Q,     // [N][T]
+                                                                int* __restrict__ argmax) {
+    extern __shared__ __align__(16) float sm[];
+    float* sWt = sm;                              // [256][128]
+    float* ssb = sWt + 256 * 128;                 // [8 groups][256][8 frames]
+    float* sred = ssb + 8 * 256 * 8;              // [8 groups][4 warps][8 frames]
+    const int n = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < 128 * 256 / 4; i += 1024) reinterpret_cast<float4*>(sWt)[i] = __ldg(d1t + i);
+    const int grp = tid >> 7, j = tid & 127, wig = (tid >> 5) & 3, lane = tid & 31;
+    const float b1 = P[P_D1B + j], w2 = P[P_D2W + j], b2 = P[P_D2B];
+    const float* hf = Hout + ((long long)n * 2 + 0) * T * 128;
+    const float* hb = Hout + ((long long)n * 2 + 1) * T * 128;
+    float* ss = ssb + grp * 256 * 8;
+    for (int t0 = 0; t0 < T; t0 += 64) {          // uniform trip count: every thread reaches every barrier
+        const int tb = t0 + grp * 8;
+        float vf[8], vb[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            const int t = tb + f;
+            vf[f] = t < T ? fmaxf(hf[(long long)t * 128 + j], 0.f) : 0.f;
+            vb[f] = t < T ? fmaxf(hb[(long long)t * 128 + j], 0.f) : 0.f;
+        }
+        __syncthreads();                          // previous pass finished reading ss / sred
+        reinterpret_cast<float4*>(ss + j * 8)[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
+        reinterpret_cast<float4*>(ss + j * 8)[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
+        reinterpret_cast<float4*>(ss + (128 + j) * 8)[0] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+        reinterpret_cast<float4*>(ss + (128 + j) * 8)[1] = make_float4(vb[4], vb[5], vb[6], vb[7]);
+        __syncthreads();
+        float acc[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) acc[f] = b1;
+#pragma unroll 4
+        for (int k = 0; k < 256; ++k) {
+            const float wv = sWt[k * 128 + j];
+            const float4 s0 = reinterpret_cast<const float4*>(ss + k * 8)[0];
+            const float4 s1 = reinterpret_cast<const float4*>(ss + k * 8)[1];
+            acc[0] = fmaf(wv, s0.x, acc[0]); acc[1] = fmaf(wv, s0.y, acc[1]);
+            acc[2] = fmaf(wv, s0.z, acc[2]); acc[3] = fmaf(wv, s0.w, acc[3]);
+            acc[4] = fmaf(wv, s1.x, acc[4]); acc[5] = fmaf(wv, s1.y, acc[5]);
+            acc[6] = fmaf(wv, s1.z, acc[6]); acc[7] = fmaf(wv, s1.w, acc[7]);
+        }
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            const float part = warp_sum(w2 * fmaxf(acc[f], 0.f));
+            if (lane == 0) sred[(grp * 4 + wig) * 8 + f] = part;
+        }
+        __syncthreads();
+        if (j < 8 && tb + j < T) {
+            const float* rp = sred + grp * 32 + j;
+            Q[(long long)n * T + tb + j] = ((rp[0] + rp[8]) + (rp[16] + rp[24])) + b2;
+        }
+    }
+    __syncthreads();
+    if (argmax && tid < 32) {   // first maximum wins (numpy argmax)
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int t = lane; t < T; t += 32) {
+            float v = Q[(long long)n * T + t];
+            if (v > best) { best = v; bi = t; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) argmax[n] = (bi == 0x7fffffff) ? 0 : bi;
+    }
 }
 
 // params / whh_pack / d1t select the network (policy or target); the save pointers are for the training step
@@ -241,14 +397,22 @@ int launch_brain_ex(ivosw_ctx* c, const float* params, const float* whh_pack, co
     brain_inproj_kernel<<<dim3(T, N), 512, 0, s>>>(params, state, T, (float*)c->brain_gi.p, sv ? sv->A1 : nullptr,
                                                    sv ? sv->E : nullptr);
     IVOSW_CUDA(cudaGetLastError());
-    const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
-    brain_recurrent_kernel<<<dim3(2, N), 512, rec_smem, s>>>((const float4*)whh_pack, (const float*)c->brain_gi.p, T, hout,
-                                                             sv ? sv->G : nullptr, sv ? sv->C : nullptr,
-                                                             sv ? sv->HP : nullptr);
-    IVOSW_CUDA(cudaGetLastError());
-    const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
-    brain_decode_kernel<<<N, 1024, dec_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
-    IVOSW_CUDA(cudaGetLastError());
+    if (sv == nullptr && getenv("IVOSW_BRAIN_LEGACY") == nullptr) {
+        brain_recurrent_cluster_kernel<<<dim3(4, 2, N), 512, 0, s>>>(params, (const float*)c->brain_gi.p, T, hout);
+        IVOSW_CUDA(cudaGetLastError());
+        const int dec8_smem = (256 * 128 + 8 * 256 * 8 + 8 * 4 * 8) * 4;
+        brain_decode8_kernel<<<N, 1024, dec8_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
+        IVOSW_CUDA(cudaGetLastError());
+    } else {
+        const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
+        brain_recurrent_kernel<<<dim3(2, N), 512, rec_smem, s>>>((const float4*)whh_pack, (const float*)c->brain_gi.p, T, hout,
+                                                                 sv ? sv->G : nullptr, sv ? sv->C : nullptr,
+                                                                 sv ? sv->HP : nullptr);
+        IVOSW_CUDA(cudaGetLastError());
+        const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
+        brain_decode_kernel<<<N, 1024, dec_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
+        IVOSW_CUDA(cudaGetLastError());
+    }
     c->launches += 3;
     return IVOSW_OK;
 }
