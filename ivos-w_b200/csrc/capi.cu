@@ -682,8 +682,21 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
     const int Tl = t_end - t_begin;
     const size_t HW = (size_t)H * W;
     int rc;
+    // chunk schedule: FC frames per chunk, tapering (halving down to 4) over the last FC frames so that the
+    // compute left over after the final copy — the only part PCIe cannot hide — is small
     const int FC = e2e_chunk_frames();
-    const int n_chunks = (Tl + FC - 1) / FC;
+    std::vector<int> bounds;
+    {
+        int pos = t_begin;
+        while (t_end - pos > FC) { bounds.push_back(pos); pos += FC; }
+        int rem = t_end - pos;
+        while (rem > 0) {
+            const int take = rem > 4 ? std::max(4, rem / 2) : rem;
+            bounds.push_back(pos); pos += take; rem -= take;
+        }
+        bounds.push_back(t_end);
+    }
+    const int n_chunks = (int)bounds.size() - 1;
     if (!c->copy_stream) IVOSW_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     while ((int)c->chunk_evts.size() < n_chunks + 1) {
         cudaEvent_t e;
@@ -699,7 +712,7 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
     IVOSW_CUDA(cudaEventRecord(c->chunk_evts[n_chunks], s));
     IVOSW_CUDA(cudaStreamWaitEvent(c->copy_stream, c->chunk_evts[n_chunks], 0));
     for (int ci = 0; ci < n_chunks; ++ci) {
-        const int c0 = t_begin + ci * FC, c1 = std::min(t_end, c0 + FC);
+        const int c0 = bounds[ci], c1 = bounds[ci + 1];
         IVOSW_CUDA(cudaMemcpyAsync(fs + (size_t)c0 * 3 * HW, frames_host + (size_t)c0 * 3 * HW,
                                    sizeof(float) * (size_t)(c1 - c0) * 3 * HW, cudaMemcpyHostToDevice, c->copy_stream));
         IVOSW_CUDA(cudaMemcpy2DAsync(ps + ((size_t)c0 * (O + 1) + 1) * HW, sizeof(float) * (size_t)(O + 1) * HW,
