@@ -213,7 +213,8 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
         }
         tk = stage_begin(c, 2, s);
         const long long launches_before = c->launches;
-        const float* x = nullptr;      // fp32 NHWC r5 handed to the pooling/FC kernel
+        const float* x = nullptr;      // fp32 NHWC r5 handed to the pooling/FC kernel (CUDA-core path)
+        SplitAct xs_final{nullptr, nullptr};   // split-fp16 r5 (tensor-core path)
         if (c->conv_mode == IVOSW_CONV_SIMT_FP32) {
             x = (const float*)c->pool.p;
             float* outs[2] = {(float*)c->actX.p, (float*)c->actY.p};
@@ -273,14 +274,14 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
                     }
                 }
             }
-            // r5 back to fp32 for the pooling/FC kernel (B x 64 x 2048: small)
-            if ((rc = launch_merge(c, xs, (float*)c->pool.p, (long long)B * 64 * 2048, terms == 3, s))) return rc;
-            x = (const float*)c->pool.p;
+            xs_final = xs;
         }
         stage_end(c, tk, s);
         if (tk >= 0) c->conv_launches_timed += c->launches - launches_before;
         tk = stage_begin(c, 3, s);
-        if ((rc = launch_gap_fc(c, x, B, score_dev + done, s))) return rc;
+        if (tc) {
+            if ((rc = launch_gap_fc_split(c, xs_final, terms == 3, B, score_dev + done, s))) return rc;
+        } else if ((rc = launch_gap_fc(c, x, B, score_dev + done, s))) return rc;
         stage_end(c, tk, s);
         c->last_chunk_b = B;
     }

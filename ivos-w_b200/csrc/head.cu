@@ -30,6 +30,51 @@ __global__ void __launch_bounds__(256) gap_fc_kernel(const float* __restrict__ r
     }
 }
 
+// Same, reading r5 directly in the split-fp16 form the tensor-core path produces (x = hi + lo / 2048):
+// no fp32 copy of r5 is materialised.  One CTA per sample, 256 threads x 8 channels, 128-bit loads.
+__global__ void __launch_bounds__(256) gap_fc_split_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                           int use_lo, const float* __restrict__ fcw, float fcb,
+                                                           float* __restrict__ score) {
+    const int b = blockIdx.x, ch0 = threadIdx.x * 8;
+    const uint4* ph = reinterpret_cast<const uint4*>(hi + (long long)b * 64 * 2048 + ch0);
+    const uint4* pl = reinterpret_cast<const uint4*>(lo + (long long)b * 64 * 2048 + ch0);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int p = 0; p < 64; ++p) {
+        const uint4 h4 = __ldg(ph + p * 256);
+        const uint4 l4 = use_lo ? __ldg(pl + p * 256) : make_uint4(0, 0, 0, 0);
+        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
+            s[2 * u] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
+            s[2 * u + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
+        }
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part = fmaf(s[k] * (1.0f / 64.0f), __ldg(fcw + ch0 + k), part);
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i];
+        score[b] = t + fcb;
+    }
+}
+
+int launch_gap_fc_split(ivosw_ctx* c, const SplitAct& r5, int use_lo, int B, float* scores, cudaStream_t s) {
+    gap_fc_split_kernel<<<B, 256, 0, s>>>(r5.hi, r5.lo, use_lo, c->fc_w, c->fc_b, scores);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
 int launch_gap_fc(ivosw_ctx* c, const float* r5, int B, float* scores, cudaStream_t s) {
     gap_fc_kernel<<<B, 256, 0, s>>>(r5, c->fc_w, c->fc_b, scores);
     c->launches += 1;

@@ -191,6 +191,7 @@ int launch_split(ivosw_ctx* c, const float* in, const SplitAct& out, long long n
 int launch_merge(ivosw_ctx* c, const SplitAct& in, float* out, long long n, int use_lo, cudaStream_t s);
 // ---- head.cu
 int launch_gap_fc(ivosw_ctx* c, const float* r5, int B, float* scores, cudaStream_t s);
+int launch_gap_fc_split(ivosw_ctx* c, const SplitAct& r5, int use_lo, int B, float* scores, cudaStream_t s);
 int launch_object_mean(ivosw_ctx* c, const float* scores, int T, int O, const double* ann_dev, double* mq_dev,
                        float* state_dev, cudaStream_t s);
 int launch_pack_state(ivosw_ctx* c, const double* mq_dev, const double* ann_dev, int T, float* state_dev,
