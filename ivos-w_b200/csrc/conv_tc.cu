@@ -250,6 +250,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
+    // overlaps the tail of the previous layer's kernel; its outputs are only touched below this point.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // tiles are walked n-fastest: the CTAs that run together share A tiles (and all weights) in L2
     if (warp == 0) {
@@ -607,7 +611,14 @@ static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P
     }
     const int tiles = P.tiles_m * P.tiles_n;
     const int grid = tiles < c->sm_count ? tiles : c->sm_count;
-    conv_tc_kernel<BN, STAGES, STAGED><<<grid, tc_threads(STAGED), S::TOTAL, s>>>(maps, P);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads(STAGED)); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = s;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !(getenv("IVOSW_PDL") && atoi(getenv("IVOSW_PDL")) == 0);
+    cfg.attrs = lattr; cfg.numAttrs = pdl ? 1 : 0;
+    IVOSW_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, STAGED>, maps, P));
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;

@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
     __syncthreads();
     tc_after();
     const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");              // (programmatic dependent launch, see conv_tc.cu)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int rows_per_band = 64 / P.bands;          // pooled rows per band
 
     if (warp == 0) {
@@ -379,7 +381,14 @@ int launch_stem_tc(ivosw_ctx* c, int B, const SplitAct& out, int terms, cudaStre
     P.out_hi = out.hi; P.out_lo = out.lo;
     P.bands = best; P.n_items = B * best; P.terms = terms;
     const int grid = P.n_items < c->sm_count ? P.n_items : c->sm_count;
-    stem_tc_kernel<<<grid, THREADS, SMEM_TOTAL, s>>>(P);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_TOTAL; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !(getenv("IVOSW_PDL") && atoi(getenv("IVOSW_PDL")) == 0);
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    IVOSW_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel, P));
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
