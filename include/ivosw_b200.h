@@ -212,6 +212,12 @@ IVOSW_API int ivosw_debug_conv(ivosw_ctx* ctx, int layer_index, int conv_mode, c
 IVOSW_API int ivosw_manet_tail(ivosw_ctx* ctx, const float* logits_dev, int T, int C, int h, int w,
                      int H, int W, float* masks_dev, float* all_p_dev, void* stream);
 
+/* utils/utils_manet.py::rough_ROI (22-39): labels_dev / out_dev B x 1 x h x w fp32 (may alias); keeps the labels
+ * inside the +-dist bounding box of the pixels != -1 and writes 0 elsewhere.  Synchronises; returns
+ * IVOSW_ERR_INVALID if an image has no such pixel (the reference raises there). */
+IVOSW_API int ivosw_rough_roi(ivosw_ctx* ctx, const float* labels_dev, float* out_dev, int B, int h, int w,
+                    int dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

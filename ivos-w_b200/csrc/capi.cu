@@ -983,4 +983,23 @@ int ivosw_manet_tail(ivosw_ctx* c, const float* logits_dev, int T, int C, int h,
     return launch_manet_tail(c, logits_dev, T, C, h, w, H, W, masks_dev, all_p_dev, (cudaStream_t)stream);
 }
 
+int ivosw_rough_roi(ivosw_ctx* c, const float* labels_dev, float* out_dev, int B, int h, int w, int dist,
+                    void* stream) {
+    IVOSW_REQUIRE(c && labels_dev && out_dev, "null pointer");
+    IVOSW_REQUIRE(B >= 1 && h >= 1 && w >= 1 && dist >= 0, "B, h, w, dist");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure(c->brain_arg, sizeof(int)))) return rc;
+    if ((rc = ensure_pinned(c, 64))) return rc;
+    if ((rc = launch_rough_roi(c, labels_dev, out_dev, B, h, w, dist, (int*)c->brain_arg.p, s))) return rc;
+    IVOSW_CUDA(cudaMemcpyAsync(c->pinned_small, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IVOSW_CUDA(cudaStreamSynchronize(s));
+    if (*(int*)c->pinned_small) {
+        set_error("rough_ROI: an image has no pixel different from -1 (the reference raises on the empty min/max)");
+        return IVOSW_ERR_INVALID;
+    }
+    return IVOSW_OK;
+}
+
 }  // extern "C"

@@ -211,6 +211,8 @@ int dqn_apply(ivosw_ctx* c, float* grad, float lr, float weight_decay, cudaStrea
 // ---- manet_tail.cu
 int launch_manet_tail(ivosw_ctx* c, const float* logits, int T, int C, int h, int w, int H, int W, float* masks,
                       float* all_p, cudaStream_t s);
+int launch_rough_roi(ivosw_ctx* c, const float* in, float* out, int B, int h, int w, int dist, int* empty_flag_dev,
+                     cudaStream_t s);
 // ---- probe helper (NHWC -> NCHW)
 int launch_nhwc_to_nchw(ivosw_ctx* c, const float* in, float* out, int B, int HW, int C, cudaStream_t s);
 

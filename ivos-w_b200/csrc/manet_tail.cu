@@ -66,4 +66,46 @@ int launch_manet_tail(ivosw_ctx* c, const float* logits, int T, int C, int h, in
     return IVOSW_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// utils/utils_manet.py::rough_ROI (22-39): first-round scribble labels are kept only inside the bounding box
+// (+-20 px) of the pixels that are not -1; everything outside becomes 0.  Slice ends are exclusive and clamp to
+// h-1 / w-1 exactly as the reference's Python slices do (SURVEY A.Q12).  One CTA per image.
+__global__ void __launch_bounds__(256) rough_roi_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                        int dist, int* __restrict__ empty_flag) {
+    __shared__ int s_mn[2], s_mx[2];
+    const int b = blockIdx.x;
+    const float* src = in + (long long)b * h * w;
+    float* dst = out + (long long)b * h * w;
+    if (threadIdx.x == 0) { s_mn[0] = s_mn[1] = 0x7fffffff; s_mx[0] = s_mx[1] = -1; }
+    __syncthreads();
+    int ymin = 0x7fffffff, xmin = 0x7fffffff, ymax = -1, xmax = -1;
+    for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+        if (src[i] != -1.0f) {
+            const int y = i / w, x = i - y * w;
+            ymin = min(ymin, y); ymax = max(ymax, y); xmin = min(xmin, x); xmax = max(xmax, x);
+        }
+    }
+    atomicMin(&s_mn[0], ymin); atomicMin(&s_mn[1], xmin); atomicMax(&s_mx[0], ymax); atomicMax(&s_mx[1], xmax);
+    __syncthreads();
+    if (s_mx[0] < 0) {      // torch.min over an empty nonzero() raises in the reference
+        if (threadIdx.x == 0) atomicExch(empty_flag, 1);
+        return;
+    }
+    const int y0 = max(s_mn[0] - dist, 0), y1 = min(s_mx[0] + dist, h - 1);   // [y0, y1) rows kept
+    const int x0 = max(s_mn[1] - dist, 0), x1 = min(s_mx[1] + dist, w - 1);
+    for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+        const int y = i / w, x = i - y * w;
+        dst[i] = (y >= y0 && y < y1 && x >= x0 && x < x1) ? src[i] : 0.0f;
+    }
+}
+
+int launch_rough_roi(ivosw_ctx* c, const float* in, float* out, int B, int h, int w, int dist, int* empty_flag_dev,
+                     cudaStream_t s) {
+    IVOSW_CUDA(cudaMemsetAsync(empty_flag_dev, 0, sizeof(int), s));
+    rough_roi_kernel<<<B, 256, 0, s>>>(in, out, h, w, dist, empty_flag_dev);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
 }  // namespace ivosw

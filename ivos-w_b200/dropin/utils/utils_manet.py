@@ -19,6 +19,11 @@ except Exception:                       # pragma: no cover - MANet checkout abse
         KNNS = 1
 
 
+def rough_ROI(ref_scribble_labels):
+    """utils/utils_manet.py:22-39 on the device (bbox reduction + masked copy in one kernel)."""
+    return get_engine(ref_scribble_labels.device).rough_roi(ref_scribble_labels, dist=20).to(ref_scribble_labels.dtype)
+
+
 def _tail(engine, logits, h, w, masks, all_P, idx):
     engine.manet_tail(logits, h, w, masks_out=masks[idx:idx + 1], all_p_out=all_P[idx:idx + 1])
     return masks[idx:idx + 1]

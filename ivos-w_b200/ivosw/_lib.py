@@ -55,6 +55,7 @@ SYMBOLS = {
     "ivosw_stage_times": (C.c_int, [C.c_void_p, _c_f, C.POINTER(C.c_longlong), C.c_int]),
     "ivosw_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_i,
                                    C.c_void_p]),
+    "ivosw_rough_roi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ivosw_manet_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -328,6 +328,14 @@ class Engine:
                                    _ptr(all_p_out if want_probs else None), _stream(self.device)))
         return masks_out, all_p_out
 
+    def rough_roi(self, labels, dist=20):
+        """utils/utils_manet.py::rough_ROI on a B x 1 x h x w CUDA tensor."""
+        x = self._dev32(labels)
+        B, _, h, w = x.shape
+        out = torch.empty_like(x)
+        check(lib.ivosw_rough_roi(self._h, _ptr(x), _ptr(out), B, h, w, dist, _stream(self.device)))
+        return out
+
     # ------------------------------------------------------------------ helpers
     def _dev32(self, t):
         if not isinstance(t, torch.Tensor):

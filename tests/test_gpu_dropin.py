@@ -111,3 +111,27 @@ def test_get_results_dropin(dropin, golden_dir):
     diff = masks.cpu().numpy().astype(np.uint8) != g["masks"]
     assert not (diff & ~near_tie).any()
     np.testing.assert_array_equal(storage.cpu().numpy().astype(np.uint8)[~near_tie], g["storage"][~near_tie])
+
+
+def test_rough_roi_dropin(dropin):
+    """utils.utils_manet.rough_ROI: same result as the reference's algorithm restated with torch ops."""
+    g = torch.Generator().manual_seed(3)
+    lab = -torch.ones((3, 1, 120, 214))
+    lab[0, 0, 40:60, 100:130] = torch.randint(0, 3, (20, 30), generator=g).float()
+    lab[1, 0, 0:5, 0:7] = 1.0
+    lab[1, 0, 110:120, 200:214] = 2.0
+    lab[2, 0, 119, 213] = 0.0
+
+    def ref(x):    # utils_manet.py:22-39
+        b, _, h, w = x.shape
+        filt = torch.zeros_like(x)
+        for i in range(b):
+            nb = (x[i] != -1).squeeze(0).nonzero()
+            (hmin, wmin), _ = torch.min(nb, 0)
+            (hmax, wmax), _ = torch.max(nb, 0)
+            filt[i, 0, max(hmin - 20, 0):min(hmax + 20, h - 1), max(wmin - 20, 0):min(wmax + 20, w - 1)] = 1
+        return torch.where(filt.bool(), x, torch.zeros_like(x))
+    out = dropin.M.rough_ROI(lab.cuda())
+    assert torch.equal(out.cpu(), ref(lab))
+    with pytest.raises(ValueError):
+        dropin.M.rough_ROI(-torch.ones((1, 1, 8, 8)).cuda())
