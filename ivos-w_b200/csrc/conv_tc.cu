@@ -107,25 +107,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// multicast form: the box lands at the same shared-memory offset in every CTA of `mask`, and each of those
-// CTAs' mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                               uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -143,12 +124,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
 // arrives on `bar` when all previously issued MMAs of this thread have completed (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// same, arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
@@ -237,13 +212,9 @@ struct TcMaps {
     CUtensorMap r_hi, r_lo, o_hi, o_lo;       // residual in / output (STAGED epilogue only)
 };
 
-// CS = CTAs per cluster (1 or 2).  With CS = 2 the two CTAs of a cluster work on neighbouring M tiles of the
-// SAME N tile: each loads its own A tiles and HALF of the weight tile, multicast to both, so the L2 -> SM
-// traffic per K block drops from 64 KB to 48 KB per SM (the 3x3 layers are bound by exactly that traffic).
-template <int BN, int STAGES_, bool STAGED_, int CS>
+template <int BN, int STAGES_, bool STAGED_>
 __global__ void __launch_bounds__(tc_threads(STAGED_), 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
-    static_assert(CS == 1 || !STAGED_, "the staged epilogue variant is not clustered");
     using S = TcSmem<BN, STAGES_, STAGED_>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -256,20 +227,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = P.tiles_m * P.tiles_n;
     const int num_kb = P.num_taps * P.cin_blocks;
-    // work list: (N tile, group of CS neighbouring M tiles), walked n-fastest by clusters; a CTA whose M tile
-    // falls off the end recomputes the last one (it must keep feeding the multicast) and stores nothing
-    const int cs_rank = CS > 1 ? (int)cluster_ctarank() : 0;
-    const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
-    const int n_work = ((P.tiles_m + CS - 1) / CS) * P.tiles_n;
-    constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1);
     const bool x3 = P.terms == 3;
     constexpr uint32_t TMEM_COLS = 4 * BN;           // 2 accumulator stages x (D0, D1)
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
         // staged variant: a slot is released by two arrivals (MMA commit + issuer, or the two epilogue leaders)
-        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], STAGED_ ? 2 : CS); }
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], STAGED_ ? 2 : 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], tc_epi_warps(STAGED_)); mbar_init(&res_bar[i], 1);
         }
@@ -282,7 +248,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     tc_fence_before();
     __syncthreads();
-    if (CS > 1) cluster_sync_all();       // peers' barriers must exist before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
@@ -297,9 +262,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = x3 ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
             const int pix_per_img = P.out_hw * P.out_hw;
-            for (int wk = cluster_id; wk < n_work; wk += n_clusters) {
-                const int nt = wk % P.tiles_n;
-                const int mt = min((wk / P.tiles_n) * CS + cs_rank, P.tiles_m - 1);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const int m0 = mt * TC_BM;
                 const int n_img = m0 / pix_per_img;
                 const int h0 = (m0 - n_img * pix_per_img) / P.out_hw;
@@ -311,17 +275,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     const int c0 = tp.c_add + cb * TC_BK;
                     tma_load_5d(st, &maps.a_hi, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
-                    if (x3) tma_load_5d(st + S::A_BYTES, &maps.a_lo, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
-                    if constexpr (CS == 1) {
-                        tma_load_2d(st + 2 * S::A_BYTES, &maps.w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
-                        if (x3) tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
-                    } else {   // this CTA's slice of the weight tile, delivered to every CTA of the cluster
-                        constexpr int ROWS = BN / CS;
-                        const int roff = cs_rank * ROWS;
-                        tma_load_2d_mc(st + 2 * S::A_BYTES + roff * 128, &maps.w_hi, &full_bar[stage], kb * TC_BK,
-                                       nt * BN + roff, MC_MASK);
-                        if (x3) tma_load_2d_mc(st + 2 * S::A_BYTES + S::B_BYTES + roff * 128, &maps.w_lo, &full_bar[stage],
-                                               kb * TC_BK, nt * BN + roff, MC_MASK);
+                    tma_load_2d(st + 2 * S::A_BYTES, &maps.w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
+                    if (x3) {
+                        tma_load_5d(st + S::A_BYTES, &maps.a_lo, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
                     }
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -351,7 +308,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int wk = cluster_id; wk < n_work; wk += n_clusters) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
@@ -373,9 +330,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
                         }
                     }
-                    // smem slot reusable once these MMAs retire (clustered: in every CTA, because the peers'
-                    // weight multicast writes into this CTA's slot too)
-                    if constexpr (CS > 1) umma_commit_mc(&empty_bar[stage], MC_MASK); else umma_commit(&empty_bar[stage]);
+                    umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
                     if constexpr (STAGED_) mbar_arrive(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
@@ -410,8 +365,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const bool relu = P.relu != 0;
             float* ss = reinterpret_cast<float*>(smem + S::SS_OFF) + grp * 128;   // [64 scale][64 shift]
             int stage = 0; uint32_t phase = 0;                  // ring position, advanced in step with the producer
-            for (int wk = cluster_id; wk < n_work; wk += n_clusters) {
-                const int nt = wk % P.tiles_n, mt = wk / P.tiles_n;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const int n0g = nt * BN + grp * 64;
                 for (int kb = 0; kb < num_kb; ++kb)             // skip this tile's operand blocks
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
@@ -495,10 +450,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
             if (leader) bulk_wait0();
         } else {
-            for (int wk = cluster_id; wk < n_work; wk += n_clusters) {
-                const int nt = wk % P.tiles_n, mt = (wk / P.tiles_n) * CS + cs_rank;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const long long m = (long long)mt * TC_BM + row;
-                const bool row_ok = mt < P.tiles_m && m < P.M;
+                const bool row_ok = m < P.M;
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * COLS);
@@ -564,8 +519,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
     }
     tc_fence_before();
-    __syncthreads();                      // (also reconverges the role-divergent warps)
-    if (CS > 1) cluster_sync_all();       // no CTA may leave while a peer can still write into it
+    __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -645,36 +599,26 @@ static int encode_out_map(CUtensorMap* map, const __half* base, long long M, int
     return encode_map(map, base, 2, dims, strides, box);
 }
 
-template <int BN, int STAGES, bool STAGED, int CS>
+template <int BN, int STAGES, bool STAGED>
 static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P, cudaStream_t s) {
     using S = TcSmem<BN, STAGES, STAGED>;
     static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
     static bool attr = false;
     if (!attr) {
-        IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STAGED, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         S::TOTAL));
         attr = true;
     }
-    const int n_work = ((P.tiles_m + CS - 1) / CS) * P.tiles_n;
-    const int max_clusters = c->sm_count / CS;
-    const int grid = (n_work < max_clusters ? n_work : max_clusters) * CS;
+    const int tiles = P.tiles_m * P.tiles_n;
+    const int grid = tiles < c->sm_count ? tiles : c->sm_count;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads(STAGED)); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = s;
-    cudaLaunchAttribute lattr[2];
-    int na = 0;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = 1;
     static const bool pdl = !(getenv("IVOSW_PDL") && atoi(getenv("IVOSW_PDL")) == 0);
-    if (pdl) {
-        lattr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        lattr[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    if (CS > 1) {
-        lattr[na].id = cudaLaunchAttributeClusterDimension;
-        lattr[na].val.clusterDim.x = CS; lattr[na].val.clusterDim.y = 1; lattr[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    cfg.attrs = lattr; cfg.numAttrs = na;
-    IVOSW_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, STAGED, CS>, maps, P));
+    cfg.attrs = lattr; cfg.numAttrs = pdl ? 1 : 0;
+    IVOSW_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, STAGED>, maps, P));
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
@@ -695,11 +639,8 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     P.M = B * L.out_hw * L.out_hw;
     if ((rc = encode_act_map(&maps.a_hi, in.hi, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
     if ((rc = encode_act_map(&maps.a_lo, in.lo, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
-    // clustered (weight-multicast) launch for the direct-epilogue variants whenever there are >= 2 M tiles
-    static const bool cluster_ok = getenv("IVOSW_NO_CLUSTER") == nullptr;
-    const int cs = (cluster_ok && !staged && (P.M + TC_BM - 1) / TC_BM >= 2) ? 2 : 1;
-    if ((rc = encode_w_map(&maps.w_hi, L.w_hi, K, L.cout, BN / cs))) return rc;
-    if ((rc = encode_w_map(&maps.w_lo, L.w_lo, K, L.cout, BN / cs))) return rc;
+    if ((rc = encode_w_map(&maps.w_hi, L.w_hi, K, L.cout, BN))) return rc;
+    if ((rc = encode_w_map(&maps.w_lo, L.w_lo, K, L.cout, BN))) return rc;
     if (staged) {
         if ((rc = encode_out_map(&maps.o_hi, out.hi, P.M, L.cout))) return rc;
         if ((rc = encode_out_map(&maps.o_lo, out.lo, P.M, L.cout))) return rc;
@@ -728,10 +669,8 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
                 t.c_add = px * L.cin; t.w_add = (ox - px) / 2;
             }
         }
-    if (staged) return launch_tc_variant<128, 3, true, 1>(c, maps, P, s);
-    if (cs == 2)
-        return BN == 128 ? launch_tc_variant<128, 3, false, 2>(c, maps, P, s) : launch_tc_variant<64, 4, false, 2>(c, maps, P, s);
-    return BN == 128 ? launch_tc_variant<128, 3, false, 1>(c, maps, P, s) : launch_tc_variant<64, 4, false, 1>(c, maps, P, s);
+    if (staged) return launch_tc_variant<128, 3, true>(c, maps, P, s);
+    return BN == 128 ? launch_tc_variant<128, 3, false>(c, maps, P, s) : launch_tc_variant<64, 4, false>(c, maps, P, s);
 }
 
 // ------------------------------------------------------------------------------------------------
