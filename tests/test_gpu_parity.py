@@ -180,3 +180,42 @@ def test_manet_tail(eng, golden_dir):
     diff = masks.cpu().numpy().astype(np.uint8) != g["masks"]
     assert not (diff & ~near_tie).any()
     assert diff.sum() <= near_tie.sum()
+
+
+def test_multi_chunk_invariance():
+    """T*O larger than the per-pass chunk (IVOSW_CHUNK): odd chunk sizes, ragged last chunk — same bits."""
+    from ivosw.engine import Engine
+    T, H, W, O = 7, 200, 300, 2
+    all_F, all_P, annotated = synth.make_clip(31, T, H, W, O)
+    ann = synth.annotated_counts(annotated, T)
+    F_d, P_d = torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda()
+    res = []
+    for chunk in ("128", "5", "1"):
+        os.environ["IVOSW_CHUNK"] = chunk
+        e = Engine(0, CONV_MODE)
+        e.load_assess(synth.assess_state_dict(0)); e.load_brain(synth.brain_state_dict(0))
+        res.append(e.round_device(F_d, P_d, ann, want_scores=True))
+        res.append(e.round_device(F_d, P_d, ann, want_scores=True))      # graph replay path
+        e.close()
+    os.environ.pop("IVOSW_CHUNK")
+    for r in res[1:]:
+        np.testing.assert_array_equal(r["scores"], res[0]["scores"])
+        assert r["next_frame"] == res[0]["next_frame"]
+
+
+def test_out_of_memory_surfaces_as_runtime_error(eng):
+    """eval_agent_manet.py:391-396 retries on RuntimeError containing 'out of memory'."""
+    B = 30000                                    # ~22 MB of workspace per unit -> far beyond 180 GB
+    tf = torch.zeros((B, 3, 8, 8), device="cuda")
+    tp = torch.zeros((B, 8, 8), device="cuda")
+    os.environ["IVOSW_CHUNK"] = "30000"
+    from ivosw.engine import Engine
+    e = Engine(0, CONV_MODE)
+    e.load_assess(synth.assess_state_dict(0))
+    with pytest.raises(RuntimeError, match="out of memory"):
+        e.assess_forward(tf, tp)
+    os.environ.pop("IVOSW_CHUNK")
+    # the context stays usable afterwards
+    s = e.assess_forward(tf[:2], tp[:2])
+    assert torch.isfinite(s).all()
+    e.close()
