@@ -306,6 +306,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = F16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -324,10 +325,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // +32 bytes inside the swizzle row
                         const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-                        umma_f16(d0, a_hi + adv, b_hi + adv, idesc, accum);
                         if (x3) {
-                            umma_f16(d1, a_hi + adv, b_lo + adv, idesc, accum);
+                            // [D0 | D1] += A_hi * [W_hi ; W_lo]^T as ONE N = 2*BN instruction (the two weight tiles are
+                            // contiguous in the stage, the two accumulators contiguous in TMEM): A_hi is read from
+                            // shared memory once instead of twice — the shared-memory port is what bounds this loop
+                            umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, accum);
                             umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+                        } else {
+                            umma_f16(d0, a_hi + adv, b_hi + adv, idesc, accum);
                         }
                     }
                     umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
