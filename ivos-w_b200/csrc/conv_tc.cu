@@ -46,6 +46,7 @@ struct TcParams {
     int out_hw;                   // OH == OW
     int tiles_m, tiles_n;
     int relu, terms;              // terms: 3 (split-fp16) or 1
+    int dbg;                      // measurement only (IVOSW_TC_DEBUG): 1 = no TMA operand loads, 2 = no MMAs
     const float* scale;
     const float* shift;
     const __half* res_hi;
@@ -272,6 +273,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     const TcTap tp = P.taps[tap];
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
+                    if (P.dbg & 1) {          // measurement: MMA + epilogue only
+                        mbar_arrive(&full_bar[stage]);
+                        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     const int c0 = tp.c_add + cb * TC_BK;
                     tma_load_5d(st, &maps.a_hi, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
@@ -325,6 +331,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // +32 bytes inside the swizzle row
                         const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                        if (P.dbg & 2) continue;      // measurement: loads + epilogue only
                         if (x3) {
                             // [D0 | D1] += A_hi * [W_hi ; W_lo]^T as ONE N = 2*BN instruction (the two weight tiles are
                             // contiguous in the stage, the two accumulators contiguous in TMEM): A_hi is read from
@@ -659,6 +666,7 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     P.out_hw = L.out_hw;
     P.tiles_m = (P.M + TC_BM - 1) / TC_BM; P.tiles_n = L.cout / BN;
     P.relu = L.relu ? 1 : 0; P.terms = terms;
+    { const char* e = getenv("IVOSW_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
     P.scale = L.scale; P.shift = L.shift;
     P.res_hi = residual ? residual->hi : nullptr; P.res_lo = residual ? residual->lo : nullptr;
     P.out_hi = out.hi; P.out_lo = out.lo;
