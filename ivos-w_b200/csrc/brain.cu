@@ -12,8 +12,8 @@
 //                           holds 32 weights), h is exchanged through distributed shared memory once per
 //                           step.  brain_recurrent_kernel (one CTA, W_hh half in registers / half in smem)
 //                           is the variant that also saves activations for the training step.
-//   brain_decode_kernel     Q_t = fc_d2(relu(fc_d1(relu([h_fw_t ; h_bw_t]))))  (agent.py:55-60) and
-//                           argmax over t, first maximum wins (numpy semantics).
+//   brain_decode8_kernel    Q_t = fc_d2(relu(fc_d1(relu([h_fw_t ; h_bw_t]))))  (agent.py:55-60), register-blocked
+//                           over 8 frames per thread, and argmax over t, first maximum wins (numpy semantics).
 //
 // Latency-bound (2T dependent steps); weights are 724 KB and stay in L2 / on chip.
 #include <cooperative_groups.h>
@@ -165,65 +165,6 @@ __global__ void brain_pack_d1t_kernel(const float* __restrict__ w, float* __rest
     out[k * 128 + j] = w[i];
 }
 
-__global__ void __launch_bounds__(1024, 1) brain_decode_kernel(const float* __restrict__ P,
-                                                               const float4* __restrict__ d1t,
-                                                               const float* __restrict__ Hout,  // [N][2][T][128]
-                                                               int T, float* __restrict__ Q,     // [N][T]
-                                                               int* __restrict__ argmax) {
-    extern __shared__ __align__(16) float sm[];
-    float* sWt = sm;                    // [256][128]: decoder_fc1.weight transposed
-    float* ss = sWt + 256 * 128;        // [8][256] relu'd concatenated state per group
-    float* sred = ss + 8 * 256;         // [8][4]
-    const int n = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < 128 * 256 / 4; i += 1024) reinterpret_cast<float4*>(sWt)[i] = __ldg(d1t + i);
-    const int g = tid >> 7, j = tid & 127, wig = (tid >> 5) & 3, lane = tid & 31;
-    const float b1 = P[P_D1B + j], w2 = P[P_D2W + j], b2 = P[P_D2B];
-    const float* hf = Hout + ((long long)n * 2 + 0) * T * 128;
-    const float* hb = Hout + ((long long)n * 2 + 1) * T * 128;
-    float* s = ss + g * 256;
-    __syncthreads();
-    for (int t0 = 0; t0 < T; t0 += 8) {   // uniform trip count: all 1024 threads hit every barrier
-        const int t = t0 + g;
-        if (t < T) {
-            s[j] = fmaxf(hf[(long long)t * 128 + j], 0.f);
-            s[128 + j] = fmaxf(hb[(long long)t * 128 + j], 0.f);
-        }
-        __syncthreads();
-        float part = 0.f;
-        if (t < T) {
-            float a0 = b1, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-            for (int k = 0; k < 256; k += 4) {
-                a0 = fmaf(sWt[(k + 0) * 128 + j], s[k + 0], a0);
-                a1 = fmaf(sWt[(k + 1) * 128 + j], s[k + 1], a1);
-                a2 = fmaf(sWt[(k + 2) * 128 + j], s[k + 2], a2);
-                a3 = fmaf(sWt[(k + 3) * 128 + j], s[k + 3], a3);
-            }
-            part = w2 * fmaxf((a0 + a1) + (a2 + a3), 0.f);
-        }
-        part = warp_sum(part);
-        if (lane == 0) sred[g * 4 + wig] = part;
-        __syncthreads();
-        if (t < T && j == 0) Q[(long long)n * T + t] = ((sred[g * 4] + sred[g * 4 + 1]) + (sred[g * 4 + 2] + sred[g * 4 + 3])) + b2;
-    }
-    __syncthreads();
-    if (argmax && tid < 32) {   // first maximum wins (numpy argmax)
-        float best = -INFINITY; int bi = 0x7fffffff;
-        for (int t = lane; t < T; t += 32) {
-            float v = Q[(long long)n * T + t];
-            if (v > best) { best = v; bi = t; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (lane == 0) argmax[n] = (bi == 0x7fffffff) ? 0 : bi;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 __global__ void brain_decode8_kernel(const float* __restrict__ P, const float4* __restrict__ d1t,
                                      const float* __restrict__ Hout, int T, float* __restrict__ Q, int* __restrict__ argmax);
 
@@ -235,9 +176,7 @@ int brain_pack(ivosw_ctx* c) {
     c->launches += 2;
     IVOSW_CUDA(cudaGetLastError());
     const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
-    const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
     IVOSW_CUDA(cudaFuncSetAttribute(brain_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_smem));
-    IVOSW_CUDA(cudaFuncSetAttribute(brain_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
     IVOSW_CUDA(cudaFuncSetAttribute(brain_decode8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (256 * 128 + 8 * 256 * 8 + 8 * 4 * 8) * 4));
     IVOSW_CUDA(cudaDeviceSynchronize());
@@ -397,22 +336,17 @@ int launch_brain_ex(ivosw_ctx* c, const float* params, const float* whh_pack, co
     brain_inproj_kernel<<<dim3(T, N), 512, 0, s>>>(params, state, T, (float*)c->brain_gi.p, sv ? sv->A1 : nullptr,
                                                    sv ? sv->E : nullptr);
     IVOSW_CUDA(cudaGetLastError());
-    if (sv == nullptr && getenv("IVOSW_BRAIN_LEGACY") == nullptr) {
+    if (sv == nullptr) {     // inference: cluster recurrence, W_hh in registers
         brain_recurrent_cluster_kernel<<<dim3(4, 2, N), 512, 0, s>>>(params, (const float*)c->brain_gi.p, T, hout);
-        IVOSW_CUDA(cudaGetLastError());
-        const int dec8_smem = (256 * 128 + 8 * 256 * 8 + 8 * 4 * 8) * 4;
-        brain_decode8_kernel<<<N, 1024, dec8_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
-        IVOSW_CUDA(cudaGetLastError());
-    } else {
+    } else {                 // training step: single-CTA recurrence that also saves gates / cell states
         const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
         brain_recurrent_kernel<<<dim3(2, N), 512, rec_smem, s>>>((const float4*)whh_pack, (const float*)c->brain_gi.p, T, hout,
-                                                                 sv ? sv->G : nullptr, sv ? sv->C : nullptr,
-                                                                 sv ? sv->HP : nullptr);
-        IVOSW_CUDA(cudaGetLastError());
-        const int dec_smem = (256 * 128 + 8 * 256 + 32) * 4;
-        brain_decode_kernel<<<N, 1024, dec_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
-        IVOSW_CUDA(cudaGetLastError());
+                                                                 sv->G, sv->C, sv->HP);
     }
+    IVOSW_CUDA(cudaGetLastError());
+    const int dec8_smem = (256 * 128 + 8 * 256 * 8 + 8 * 4 * 8) * 4;
+    brain_decode8_kernel<<<N, 1024, dec8_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
+    IVOSW_CUDA(cudaGetLastError());
     c->launches += 3;
     return IVOSW_OK;
 }

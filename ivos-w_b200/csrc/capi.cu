@@ -156,7 +156,18 @@ static int ensure_workspace(ivosw_ctx* c, int cap) {
     int rc;
     const size_t f = sizeof(float);
     if ((rc = ensure(c->boxes, (size_t)cap * 4 * f))) return rc;
-    if ((rc = ensure(c->crop, (size_t)cap * ROI * ROI * 4 * f))) return rc;
+    if (c->conv_mode == IVOSW_CONV_SIMT_FP32) {
+        if ((rc = ensure(c->crop, (size_t)cap * ROI * ROI * 4 * f))) return rc;
+    } else {
+        // padded split-fp16 crop planes; the zero border is written once per (re)allocation and never touched again
+        const size_t plane = (size_t)cap * CROP_PH * CROP_PW * 8;
+        if (c->crop_hi.bytes < plane || c->crop_lo.bytes < plane) {
+            if ((rc = ensure(c->crop_hi, plane))) return rc;
+            if ((rc = ensure(c->crop_lo, plane))) return rc;
+            IVOSW_CUDA(cudaMemset(c->crop_hi.p, 0, c->crop_hi.bytes));
+            IVOSW_CUDA(cudaMemset(c->crop_lo.p, 0, c->crop_lo.bytes));
+        }
+    }
     if ((rc = ensure(c->c1, (size_t)cap * 128 * 128 * 64 * f))) return rc;
     if ((rc = ensure(c->pool, (size_t)cap * 64 * 64 * 64 * f))) return rc;
     const size_t big = (size_t)cap * 64 * 64 * 256 * f;   // largest block output (res2)
@@ -190,12 +201,17 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
         ua.u0 = u_first + done;
         int tk = stage_begin(c, 0, s);
         if ((rc = launch_bbox(c, ua, B, H, W, s))) return rc;
-        if ((rc = launch_roi_sample(c, ua, B, H, W, boxes_dev ? boxes_dev + 4 * (size_t)done : (float*)c->boxes.p, s)))
-            return rc;
-        stage_end(c, tk, s);
-        if ((rc = keep_probe(c, 0, (const float*)c->crop.p, (size_t)B * ROI * ROI * 4, s))) return rc;
         const bool tc = c->conv_mode != IVOSW_CONV_SIMT_FP32;
         const int terms = c->conv_mode == IVOSW_CONV_TC_FP16X3 ? 3 : 1;
+        if ((rc = launch_roi_sample(c, ua, B, H, W, boxes_dev ? boxes_dev + 4 * (size_t)done : (float*)c->boxes.p, tc, s)))
+            return rc;
+        stage_end(c, tk, s);
+        if (c->probes_on) {
+            if (tc) {
+                if ((rc = ensure(c->probe_buf[0], (size_t)B * ROI * ROI * 4 * sizeof(float)))) return rc;
+                if ((rc = launch_crop_merge(c, (float*)c->probe_buf[0].p, B, terms == 3, s))) return rc;
+            } else if ((rc = keep_probe(c, 0, (const float*)c->crop.p, (size_t)B * ROI * ROI * 4, s))) return rc;
+        }
         SplitAct xs = split_view(c->c1);     // tensor-core path: pooled stem output as split-fp16 planes
         tk = stage_begin(c, 1, s);
         if (tc) {
@@ -430,7 +446,7 @@ void ivosw_destroy(ivosw_ctx* c) {
         if (L.w_lo) cudaFree(L.w_lo);
     }
     DeviceBuffer* bufs[] = {&c->brain_gi, &c->brain_h, &c->brain_state, &c->brain_q, &c->brain_arg, &c->bbox_min,
-                            &c->bbox_max, &c->boxes, &c->crop, &c->c1, &c->pool, &c->actX, &c->actY, &c->actDS,
+                            &c->bbox_max, &c->boxes, &c->crop, &c->crop_hi, &c->crop_lo, &c->c1, &c->pool, &c->actX, &c->actY, &c->actDS,
                             &c->actT1, &c->actT2, &c->scores, &c->scores_all, &c->mq, &c->stage_frames, &c->stage_probs};
     for (DeviceBuffer* b : bufs) release(*b);
     for (DeviceBuffer& b : c->probe_buf) release(b);
@@ -444,10 +460,6 @@ void ivosw_destroy(ivosw_ctx* c) {
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaEvent_t e : c->chunk_evts) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) {
-        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
-        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
-    }
     delete c;
 }
 

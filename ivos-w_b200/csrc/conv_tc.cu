@@ -224,8 +224,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint64_t* empty_bar = bars + S::STAGES;          // [STAGES]
     uint64_t* tfull_bar = bars + 2 * S::STAGES;      // [2]
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2; // [2]
-    uint64_t* res_bar = bars + 2 * S::STAGES + 4;    // [2] residual tile landed (STAGED)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 6);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = P.tiles_m * P.tiles_n;
@@ -238,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // staged variant: a slot is released by two arrivals (MMA commit + issuer, or the two epilogue leaders)
         for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], STAGED_ ? 2 : 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], tc_epi_warps(STAGED_)); mbar_init(&res_bar[i], 1);
+            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], tc_epi_warps(STAGED_));
         }
         fence_barrier_init();
     }

@@ -12,6 +12,8 @@
 namespace ivosw {
 
 constexpr int ROI = 256;           // models/assessment.py:170 dst_size
+constexpr int CROP_PH = 262;       // zero-bordered crop canvas of the tensor-core stem: image at (3, 3),
+constexpr int CROP_PW = 264;       //   rows -3..258, columns -3..260 of the 7x7 stride-2 pad-3 convolution
 constexpr float BN_EPS = 1e-5f;    // torch BatchNorm2d default
 constexpr int BRAIN_H = 128;       // models/agent.py:14 hidden_channels
 constexpr int BRAIN_G = 4 * BRAIN_H;
@@ -119,6 +121,7 @@ struct ivosw_ctx {
 
     // workspace (grown on demand, per chunk of `chunk_cap` samples)
     int chunk_cap = 0;
+    ivosw::DeviceBuffer crop_hi, crop_lo;   // tensor-core path: padded split-fp16 crop planes (roi.cu)
     ivosw::DeviceBuffer bbox_min, bbox_max, boxes, crop, c1, pool, actX, actY, actDS, actT1, actT2, scores, mq;
     // what the probe entry point can read back (valid for the last chunk processed)
     bool probes_on = false;
@@ -160,8 +163,6 @@ struct ivosw_ctx {
     void* pinned_small = nullptr;    // small pinned scratch for D2H results
     size_t pinned_small_bytes = 0;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr};
 };
 
 namespace ivosw {
@@ -175,7 +176,9 @@ void release(DeviceBuffer& b);
 
 // ---- roi.cu
 int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s);
-int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, cudaStream_t s);
+int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, bool split,
+                      cudaStream_t s);
+int launch_crop_merge(ivosw_ctx* c, float* out, int B, int use_lo, cudaStream_t s);
 // ---- stem.cu
 int launch_stem(ivosw_ctx* c, int B, cudaStream_t s);
 // ---- stem_tc.cu

@@ -128,9 +128,16 @@ __device__ inline float lin256(int i) {
 
 constexpr int ROI_ROWS_PER_CTA = 8;
 
+// SPLIT = false: crop is [B][256][256] float4 (fp32 validation path).
+// SPLIT = true : crop is written directly in the form the tensor-core stem consumes — two fp16 planes
+//                (hi, lo with x = hi + lo/2048), 4 channels = 8 bytes per pixel, on a zero-bordered canvas of
+//                CROP_PH x CROP_PW pixels with the image at offset (3, 3): the 7x7/2 stem's padding is then
+//                physical and every 2-pixel K slab of the stem's A operand is one aligned 16-byte load.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) roi_sample_kernel(UnitAddr ua, int H, int W, const int2* __restrict__ mn,
                                                          const int2* __restrict__ mx, float3 mean, float3 stdv,
-                                                         float* __restrict__ boxes, float4* __restrict__ crop) {
+                                                         float* __restrict__ boxes, float4* __restrict__ crop,
+                                                         uint2* __restrict__ crop_hi, uint2* __restrict__ crop_lo) {
     __shared__ float th[4];
     const int b = blockIdx.y;
     if (threadIdx.x == 0) {
@@ -190,17 +197,55 @@ __global__ void __launch_bounds__(256) roi_sample_kernel(UnitAddr ua, int H, int
         out[0] = __fdiv_rn(__fsub_rn(out[0], mean.x), stdv.x);
         out[1] = __fdiv_rn(__fsub_rn(out[1], mean.y), stdv.y);
         out[2] = __fdiv_rn(__fsub_rn(out[2], mean.z), stdv.z);
-        crop[((long long)b * ROI + oy) * ROI + ox] = make_float4(out[0], out[1], out[2], out[3]);
+        if (SPLIT) {
+            const __half2 h01 = __floats2half2_rn(out[0], out[1]), h23 = __floats2half2_rn(out[2], out[3]);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn((out[0] - f01.x) * 2048.0f, (out[1] - f01.y) * 2048.0f);
+            const __half2 l23 = __floats2half2_rn((out[2] - f23.x) * 2048.0f, (out[3] - f23.y) * 2048.0f);
+            const long long pix = ((long long)b * CROP_PH + oy + 3) * CROP_PW + ox + 3;
+            crop_hi[pix] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            crop_lo[pix] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        } else {
+            crop[((long long)b * ROI + oy) * ROI + ox] = make_float4(out[0], out[1], out[2], out[3]);
+        }
     }
 }
 
-int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, cudaStream_t s) {
+int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, bool split,
+                      cudaStream_t s) {
     dim3 grid(ROI / ROI_ROWS_PER_CTA, B);
-    roi_sample_kernel<<<grid, 256, 0, s>>>(ua, H, W, (const int2*)c->bbox_min.p,
-                                           (const int2*)c->bbox_max.p,
-                                           make_float3(c->mean[0], c->mean[1], c->mean[2]),
-                                           make_float3(c->stdv[0], c->stdv[1], c->stdv[2]), boxes_out,
-                                           (float4*)c->crop.p);
+    const float3 mean = make_float3(c->mean[0], c->mean[1], c->mean[2]);
+    const float3 stdv = make_float3(c->stdv[0], c->stdv[1], c->stdv[2]);
+    if (split)
+        roi_sample_kernel<true><<<grid, 256, 0, s>>>(ua, H, W, (const int2*)c->bbox_min.p, (const int2*)c->bbox_max.p, mean,
+                                                     stdv, boxes_out, nullptr, (uint2*)c->crop_hi.p, (uint2*)c->crop_lo.p);
+    else
+        roi_sample_kernel<false><<<grid, 256, 0, s>>>(ua, H, W, (const int2*)c->bbox_min.p, (const int2*)c->bbox_max.p, mean,
+                                                      stdv, boxes_out, (float4*)c->crop.p, nullptr, nullptr);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+// probe helper: padded split-fp16 crop planes -> [B][256][256][4] fp32
+__global__ void crop_merge_kernel(const uint2* __restrict__ hi, const uint2* __restrict__ lo, float4* __restrict__ out,
+                                  long long total, int use_lo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ox = (int)(i % ROI), oy = (int)((i / ROI) % ROI);
+    const long long b = i / (ROI * ROI);
+    const long long pix = (b * CROP_PH + oy + 3) * CROP_PW + ox + 3;
+    const uint2 h = hi[pix], l = use_lo ? lo[pix] : make_uint2(0, 0);
+    const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+    out[i] = make_float4(fmaf(l01.x, 1.0f / 2048.0f, h01.x), fmaf(l01.y, 1.0f / 2048.0f, h01.y),
+                         fmaf(l23.x, 1.0f / 2048.0f, h23.x), fmaf(l23.y, 1.0f / 2048.0f, h23.y));
+}
+
+int launch_crop_merge(ivosw_ctx* c, float* out, int B, int use_lo, cudaStream_t s) {
+    const long long total = (long long)B * ROI * ROI;
+    crop_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint2*)c->crop_hi.p, (const uint2*)c->crop_lo.p,
+                                                                      (float4*)out, total, use_lo);
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;

@@ -5,11 +5,12 @@
 //
 // GEMM view per CTA tile: M = 128 = one full output row of c1 (ow = 0..127), N = 64 channels,
 // K = 7 filter rows x 32 (7 kw x 4 channels + 4 zero pad) = 224.  The 4-channel pixels are far too
-// narrow for a TMA box, so the A operand is built by the SM: "builder" warps read the fp32 crop
-// (two adjacent pixels = 32 bytes per 8-element K slab), split every value into the fp16 (hi, lo)
-// pair used by conv_tc.cu and store it in the canonical no-swizzle K-major UMMA layout (8 x 16 B
-// core matrices); a proxy fence hands the tile to tcgen05.mma.  Weights (hi/lo, 56 KB) are packed on
-// the host into the same layout and stay resident in shared memory for the whole kernel.
+// narrow for a TMA box, so the A operand is built by the SM: the ROI sampler already wrote the crop as
+// split-fp16 planes on a zero-bordered canvas (roi.cu), so a K slab (two adjacent pixels x 4 channels)
+// is ONE aligned 16-byte load per plane; "builder" warps copy slabs into the canonical no-swizzle
+// K-major UMMA layout (8 x 16 B core matrices) and a proxy fence hands the tile to tcgen05.mma.
+// Weights (hi/lo, 56 KB) are packed on the host into the same layout and stay resident in shared
+// memory for the whole kernel.
 //
 // A CTA walks consecutive c1 rows of one image band, so the epilogue can fuse the 3x3/2 max-pool:
 // each BN+ReLU'd c1 row goes to a shared-memory row buffer, is pooled horizontally, and a running
@@ -33,7 +34,7 @@ constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + 2 * A_PLANE;               // 114688
 constexpr int OFF_ROW = OFF_B + 2 * B_PLANE;             // 172032
 constexpr int OFF_BAR = OFF_ROW + ROWBUF;                // 204800
-constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
+constexpr int SMEM_TOTAL = OFF_BAR + 128 + 512 + 1024;     // barriers, scale/shift, alignment slack
 constexpr long long WAIT_TIMEOUT = 4000000000ll;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -93,7 +94,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 }
 
 struct Params {
-    const float4* crop;        // [B][256][256] float4
+    const uint4* crop_hi;      // [B][CROP_PH][CROP_PW / 2] : two pixels x 4 channels fp16 per 16 bytes
+    const uint4* crop_lo;
     const uint4* wpack;        // 2 * B_PLANE bytes: hi plane then lo plane, already in the smem image layout
     const float* scale;
     const float* shift;
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
     // weights: plain 16-byte copies of the pre-packed smem image
     for (int i = threadIdx.x; i < 2 * B_PLANE / 16; i += THREADS)
         reinterpret_cast<uint4*>(smem + OFF_B)[i] = __ldg(P.wpack + i);
+    float* sss = reinterpret_cast<float*>(smem + OFF_BAR + 128);        // [64 scale][64 shift] (bn1 folded)
+    if (threadIdx.x < 128) sss[threadIdx.x] = threadIdx.x < 64 ? P.scale[threadIdx.x] : P.shift[threadIdx.x - 64];
     if (threadIdx.x == 0) {
         mb_init(&a_full[0], 4); mb_init(&a_full[1], 4); mb_init(&a_empty[0], 1); mb_init(&a_empty[1], 1);
         mb_init(&t_full[0], 1); mb_init(&t_full[1], 1); mb_init(&t_empty[0], 4); mb_init(&t_empty[1], 4);
@@ -183,40 +187,27 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
     } else if (warp >= 8) {
         // ------------------------------------------------ A builders (256 threads)
         // thread -> one c1 column (ow) and one K part: part 0 = filter rows 0..3, part 1 = rows 4..6.
-        // A filter row needs the 7 crop pixels 2*ow-3 .. 2*ow+3 (112 contiguous bytes); two filter rows
-        // (14 loads) are in flight at a time, and the first pair is issued before waiting for the slot.
+        // Filter row kh of output (oh, ow) is canvas row 2*oh + kh, canvas pixels 2*ow .. 2*ow + 7: four
+        // aligned 16-byte slabs per plane.  The first two filter rows are loaded before waiting for the slot.
         const int bt = threadIdx.x - 256;
         const int ow = bt & 127, part = bt >> 7;
         const int kh0 = part * 4, nkh = part == 0 ? 4 : 3;
-        const int ix0 = 2 * ow - 3;
         uint32_t e_phase = 0;
-        auto load_row = [&](const float4* im, int oh, int kh, float4* px) {
-            const int iy = 2 * oh - 3 + kh;
+        const uint32_t sA = (uint32_t)((ow >> 3) * 128 + (ow & 7) * 16);
+        auto load_row = [&](const uint4* ph, const uint4* pl, int oh, int kh, uint4* vh, uint4* vl) {
+            const size_t idx = ((size_t)(2 * oh + kh) * CROP_PW + 2 * ow) >> 1;
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                const int ix = ix0 + j;
-                px[j] = (iy >= 0 && iy < ROI && ix >= 0 && ix < ROI) ? __ldg(im + iy * ROI + ix) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < 4; ++sp) {
+                vh[sp] = __ldg(ph + idx + sp);
+                if (x3) vl[sp] = __ldg(pl + idx + sp);
             }
         };
-        auto store_row = [&](int kh, const float4* px) {
+        auto store_row = [&](int kh, const uint4* vh, const uint4* vl) {
 #pragma unroll
-            for (int sp = 0; sp < 4; ++sp) {              // slab = pixel pair (2sp, 2sp+1); the 8th pixel is zero pad
-                const float4 a4 = px[2 * sp];
-                const float4 b4 = sp < 3 ? px[2 * sp + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float v[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float a = fminf(fmaxf(v[2 * u], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * u + 1], -65504.f), 65504.f);
-                    const __half2 h = __floats2half2_rn(a, b);
-                    const float2 hf = __half22float2(h);
-                    hi[u] = *reinterpret_cast<const uint32_t*>(&h);
-                    lo[u] = pack2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
-                }
-                const int sl = kh * 4 + sp;
-                const uint32_t off = (uint32_t)((sl * 16 + (ow >> 3)) * 128 + (ow & 7) * 16);
-                *reinterpret_cast<uint4*>(smem + OFF_A + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (x3) *reinterpret_cast<uint4*>(smem + OFF_A + A_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int sp = 0; sp < 4; ++sp) {
+                const uint32_t off = (uint32_t)((kh * 4 + sp) * 2048) + sA;
+                *reinterpret_cast<uint4*>(smem + OFF_A + off) = vh[sp];
+                if (x3) *reinterpret_cast<uint4*>(smem + OFF_A + A_PLANE + off) = vl[sp];
             }
         };
         for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
@@ -224,19 +215,20 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
             const int p0 = band * rows_per_band;
             const int r_first = band == 0 ? 0 : 2 * p0 - 1;              // first c1 row of the band
             const int n_rows = 2 * rows_per_band + (band == 0 ? 0 : 1);
-            const float4* im = P.crop + (size_t)img * ROI * ROI;
+            const uint4* ph = P.crop_hi + (size_t)img * CROP_PH * CROP_PW / 2;
+            const uint4* pl = P.crop_lo + (size_t)img * CROP_PH * CROP_PW / 2;
             for (int r = 0; r < n_rows; ++r) {
                 const int oh = r_first + r;
-                float4 pa[7], pb[7];
-                load_row(im, oh, kh0, pa);
-                load_row(im, oh, kh0 + 1, pb);
+                uint4 ah[4], al[4], bh[4], bl[4];
+                load_row(ph, pl, oh, kh0, ah, al);
+                load_row(ph, pl, oh, kh0 + 1, bh, bl);
                 mb_wait(&a_empty[part], e_phase ^ 1);
-                store_row(kh0, pa);
-                store_row(kh0 + 1, pb);
-                load_row(im, oh, kh0 + 2, pa);
-                if (nkh == 4) load_row(im, oh, kh0 + 3, pb);
-                store_row(kh0 + 2, pa);
-                if (nkh == 4) store_row(kh0 + 3, pb);
+                store_row(kh0, ah, al);
+                store_row(kh0 + 1, bh, bl);
+                load_row(ph, pl, oh, kh0 + 2, ah, al);
+                if (nkh == 4) load_row(ph, pl, oh, kh0 + 3, bh, bl);
+                store_row(kh0 + 2, ah, al);
+                if (nkh == 4) store_row(kh0 + 3, bh, bl);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mb_arrive(&a_full[part]);
@@ -275,12 +267,14 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
 #pragma unroll
                     for (int k4 = 0; k4 < 8; ++k4) {
                         float o[4];
+                        const float4 sc4 = *reinterpret_cast<const float4*>(sss + cc + k4 * 4);
+                        const float4 sh4 = *reinterpret_cast<const float4*>(sss + 64 + cc + k4 * 4);
+                        const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int ch = cc + k4 * 4 + u;
                             float a = __uint_as_float(r0[k4 * 4 + u]);
                             if (x3) a = fmaf(__uint_as_float(r1[k4 * 4 + u]), 1.0f / 2048.0f, a);
-                            o[u] = fmaxf(fmaf(a, __ldg(P.scale + ch), __ldg(P.shift + ch)), 0.f);    // bn1 + relu
+                            o[u] = fmaxf(fmaf(a, scv[u], shv[u]), 0.f);    // bn1 + relu
                         }
                         rowbuf[((cc >> 2) + k4) * 128 + ow] = make_float4(o[0], o[1], o[2], o[3]);
                     }
@@ -376,7 +370,7 @@ int launch_stem_tc(ivosw_ctx* c, int B, const SplitAct& out, int terms, cudaStre
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nb; }
     }
     Params P;
-    P.crop = (const float4*)c->crop.p; P.wpack = (const uint4*)c->stem_wpack;
+    P.crop_hi = (const uint4*)c->crop_hi.p; P.crop_lo = (const uint4*)c->crop_lo.p; P.wpack = (const uint4*)c->stem_wpack;
     P.scale = c->stem_scale; P.shift = c->stem_shift;
     P.out_hi = out.hi; P.out_lo = out.lo;
     P.bands = best; P.n_items = B * best; P.terms = terms;
