@@ -981,7 +981,12 @@ int ivosw_debug_conv(ivosw_ctx* c, int li, int conv_mode, const float* in_dev, c
     const int terms = conv_mode == IVOSW_CONV_TC_FP16X3 ? 3 : 1;
     if ((rc = launch_split(c, in_dev, xin, (long long)n_in, s))) return rc;
     if (residual_dev && (rc = launch_split(c, residual_dev, res, (long long)n_out, s))) return rc;
-    if ((rc = launch_conv_tc(c, L, xin, residual_dev ? &res : nullptr, yout, B, terms, s))) return rc;
+    // measurement only: IVOSW_DEBUG_CONV_REPEAT = n launches the (idempotent) layer n times, so that the
+    // difference between two n isolates the convolution kernel from the split / merge helpers
+    int reps = 1;
+    if (const char* e = getenv("IVOSW_DEBUG_CONV_REPEAT")) reps = atoi(e) > 1 ? atoi(e) : 1;
+    for (int r = 0; r < reps; ++r)
+        if ((rc = launch_conv_tc(c, L, xin, residual_dev ? &res : nullptr, yout, B, terms, s))) return rc;
     return launch_merge(c, yout, out_dev, (long long)n_out, terms == 3, s);
 }
 

@@ -46,7 +46,7 @@ struct TcParams {
     int out_hw;                   // OH == OW
     int tiles_m, tiles_n;
     int relu, terms;              // terms: 3 (split-fp16) or 1
-    int dbg;                      // measurement only (IVOSW_TC_DEBUG): 1 = no TMA operand loads, 2 = no MMAs
+    int dbg;                      // measurement only (IVOSW_TC_DEBUG): 1 = no TMA operand loads, 2 = no MMAs, 4 = no staged epilogue work
     const float* scale;
     const float* shift;
     const __half* res_hi;
@@ -175,6 +175,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id, int nthreads) {
@@ -189,23 +190,31 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// STAGED epilogue (the 1x1 "expand" layers, whose output + residual traffic dominates): per tile the
-// producer pushes one extra 64 KB block through the SAME shared-memory ring as the operand blocks — the
-// residual tile (hi/lo planes of both column halves, 128B-swizzled), prefetched by TMA while the
-// previous tile is still in its epilogue.  The epilogue groups rewrite that block in place with the
-// output, a TMA store sends it back, and the slot returns to the ring once the store has read it.
-// Deep memory-level parallelism and fully coalesced traffic instead of per-thread 16-byte accesses.
+// STAGED epilogue (the 1x1 "expand" layers, whose output + residual traffic dominates).  Next to the
+// operand ring sits one 32 KB staging buffer (hi + lo planes of a 128 x 64 half tile, 128B-swizzled).  Per
+// tile the 16 epilogue warps make two passes (column halves): accumulators come out of TMEM, BN + residual
+// + ReLU + the hi/lo split happen in registers, the half tile is written to the staging buffer and ONE
+// elected thread sends it back with two TMA stores — fully coalesced 128-byte rows instead of per-thread
+// 16-byte stores.
+// The residual tile (64 KB) travels through the operand ring as one extra block per tile, fetched by TMA
+// (coalesced, deep memory-level parallelism) and signalled on its own barrier pair; the epilogue warps copy
+// it into registers as soon as it lands — one tile ahead of its use, right after the previous tile's
+// epilogue — and hand the slot straight back, so the block never starves the main loop of ring slots.
+// (The first version rewrote the residual block in place and held the slot until the output store had
+// read it; with 2 or 4 K blocks per tile on a 3-slot ring that serialised every tile on one residual
+// round trip.  A version with per-thread residual loads from global memory was 2x slower on res2:
+// 32 rows x 16 bytes per warp instruction is the uncoalesced pattern.  profiles/r1_tc_ceiling.md.)
 template <int BN, int STAGES_, bool STAGED_>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = STAGES_;
-    static constexpr int STG_GROUP_BYTES = 2 * TC_BM * 64 * 2;   // hi + lo planes of a 128 x 64 half tile: 32 KB
-    static_assert(!STAGED_ || STAGE_BYTES == 2 * STG_GROUP_BYTES, "an epilogue block must fill exactly one ring slot");
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int SS_OFF = BAR_OFF + 256;           // scale/shift staging: 2 groups x 128 floats
-    static constexpr int TOTAL = SS_OFF + 1024 + 1024 /*align slack*/;
+    static constexpr int STG_OFF = STAGES * STAGE_BYTES;                 // 1024-byte aligned (128B swizzle atom)
+    static constexpr int NSTG = STAGES_ == 2 ? 2 : 1;                    // a 2-slot ring leaves room for a second buffer
+    static constexpr int STG_BYTES = STAGED_ ? NSTG * 2 * TC_BM * 64 * 2 : 0;   // 32 KB each
+    static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024 /*align slack*/;
 };
 
 struct TcMaps {
@@ -225,6 +234,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint64_t* tfull_bar = bars + 2 * S::STAGES;      // [2]
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+    uint64_t* res_full = bars + 2 * S::STAGES + 5;   // [2] residual block of tile t landed (t & 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = P.tiles_m * P.tiles_n;
@@ -234,10 +244,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
-        // staged variant: a slot is released by two arrivals (MMA commit + issuer, or the two epilogue leaders)
-        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], STAGED_ ? 2 : 1); }
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], tc_epi_warps(STAGED_));
+            mbar_init(&res_full[i], 1);
         }
         fence_barrier_init();
     }
@@ -262,6 +272,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = x3 ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
             const int pix_per_img = P.out_hw * P.out_hw;
+            int t_local = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const int m0 = mt * TC_BM;
@@ -288,21 +299,22 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
                 if constexpr (STAGED_) {
-                    // epilogue block: residual tile of both column halves (or just the slot, for staging the output)
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* st = smem + stage * S::STAGE_BYTES;
                     if (P.res_hi != nullptr) {
-                        mbar_expect_tx(&full_bar[stage], (x3 ? 4u : 2u) * TC_BM * 128);
+                        // residual block of this tile: both column halves, hi/lo planes; completion goes to
+                        // res_full — the slot's own full barrier is not involved (the MMA issuer keeps a parity
+                        // bit per slot and only counts the uses it waits on)
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * S::STAGE_BYTES;
+                        uint64_t* rb = &res_full[t_local & 1];
+                        mbar_expect_tx(rb, (x3 ? 4u : 2u) * TC_BM * 128);
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
-                            tma_load_2d(st + g * S::STG_GROUP_BYTES, &maps.r_hi, &full_bar[stage], nt * BN + g * 64, m0);
-                            if (x3) tma_load_2d(st + g * S::STG_GROUP_BYTES + TC_BM * 128, &maps.r_lo, &full_bar[stage],
-                                                nt * BN + g * 64, m0);
+                            tma_load_2d(st + g * 2 * TC_BM * 128, &maps.r_hi, rb, nt * BN + g * 64, m0);
+                            if (x3) tma_load_2d(st + g * 2 * TC_BM * 128 + TC_BM * 128, &maps.r_lo, rb, nt * BN + g * 64, m0);
                         }
-                    } else {
-                        mbar_arrive(&full_bar[stage]);
+                        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                    ++t_local;
                 }
             }
         }
@@ -312,7 +324,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             // instruction descriptor: D = F32, A = B = F16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
+            int stage = 0; uint32_t full_bits = 0;               // parity of the next operand block, per slot
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator stage
@@ -320,7 +332,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
                 const uint32_t d1 = d0 + BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(&full_bar[stage], (full_bits >> stage) & 1u);
+                    full_bits ^= 1u << stage;
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * S::STAGE_BYTES);
                     const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + S::A_BYTES);
@@ -342,16 +355,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         }
                     }
                     umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
-                    if constexpr (STAGED_) mbar_arrive(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == S::STAGES) stage = 0;
                 }
                 if constexpr (STAGED_) {
-                    // The tile's epilogue block is not ours, but we must see it land before moving on: a
-                    // parity test on this slot's NEXT use (an operand block, three positions later) would
-                    // otherwise pass prematurely while the residual TMA of this generation is still in flight.
-                    mbar_wait(&full_bar[stage], phase);
-                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                    if (P.res_hi != nullptr) {                   // step over the residual block's ring position
+                        if (++stage == S::STAGES) stage = 0;
+                    }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -366,46 +376,85 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         int acc = 0; uint32_t acc_phase = 0;
         if constexpr (STAGED_) {
             static_assert(!STAGED_ || BN == 128, "staged epilogue is built for 128-column tiles");
-            // 16 warps: quarter = TMEM lane quarter, colq = which 32-column quarter of the 128-column tile;
-            // colq 0,1 form group 0 (columns 0..63, one 64-column TMA box), colq 2,3 group 1.
-            const int colq = e >> 2;
-            const int grp = colq >> 1;
-            const int gt = ((colq & 1) * 4 + (e & 3)) * 32 + lane;      // 0..255 inside the group
-            const bool leader = gt == 0;
+            // 16 warps: quarter = TMEM lane quarter (a hardware rule: warp % 4), csub = which 16-column slice
+            // of the 64-column pass this warp owns
+            const int csub = e >> 2;
+            const bool leader = threadIdx.x == 64;
             const bool has_res = P.res_hi != nullptr;
             const bool relu = P.relu != 0;
-            float* ss = reinterpret_cast<float*>(smem + S::SS_OFF) + grp * 128;   // [64 scale][64 shift]
-            int stage = 0; uint32_t phase = 0;                  // ring position, advanced in step with the producer
+            // (with two staging buffers — the K = 64 layers on a 2-slot ring — pass g owns buffer g and only waits
+            //  for its own store of the previous tile)
+            uint32_t soff[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) soff[q] = (uint32_t)row * 128u + (uint32_t)(((2 * csub + q) ^ (row & 7)) << 4);
+            float rf[2][16];                                    // this thread's residual values: [pass][column]
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) rf[g][k] = 0.f;
+            int stage = 0, t_local = 0;                         // ring position of the residual blocks
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
-                const int n0g = nt * BN + grp * 64;
-                for (int kb = 0; kb < num_kb; ++kb)             // skip this tile's operand blocks
-                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
-                uint8_t* stg = smem + stage * S::STAGE_BYTES + grp * S::STG_GROUP_BYTES;
-                const uint32_t stg_hi = smem_u32(stg), stg_lo = stg_hi + TC_BM * 128;
-                if (gt < 128) ss[gt] = gt < 64 ? __ldg(P.scale + n0g + gt) : __ldg(P.shift + n0g + gt - 64);
-                group_bar(1 + grp, 256);
-                // Order matters: this role skips the operand blocks without waiting on them, so it may only
-                // test the epilogue block's barrier once the tile's MMAs are known to be complete — that
-                // guarantees every earlier use of the slot has finished and the parity test cannot alias
-                // with the previous generation of the barrier.
+                if (has_res) {
+                    // residual tile -> registers (every epilogue thread waits on every use of res_full, in order),
+                    // then the slot goes straight back to the producer
+                    stage = (stage + num_kb) % S::STAGES;
+                    mbar_wait(&res_full[t_local & 1], (uint32_t)(t_local >> 1) & 1u);
+                    const uint32_t rs = smem_u32(smem + stage * S::STAGE_BYTES);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint4 h4 = lds128(rs + g * 2 * TC_BM * 128 + soff[q]);
+                            const uint4 l4 = x3 ? lds128(rs + g * 2 * TC_BM * 128 + TC_BM * 128 + soff[q]) : make_uint4(0, 0, 0, 0);
+                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
+                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
+                                rf[g][q * 8 + u * 2 + 0] = fmaf(lf.x, 1.0f / 2048.0f, hf.x);
+                                rf[g][q * 8 + u * 2 + 1] = fmaf(lf.y, 1.0f / 2048.0f, hf.y);
+                            }
+                        }
+                    // The slot is about to be overwritten by TMA (async proxy): the generic-proxy reads above must be
+                    // complete first.  A barrier alone orders them against other threads' generic accesses only —
+                    // releasing right after it let the next block land under still-queued reads.
+                    fence_proxy_async();
+                    group_bar(3, 512);
+                    if (leader) mbar_arrive(&empty_bar[stage]);
+                    stage = (stage + 1) % S::STAGES;
+                    ++t_local;
+                }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
-                mbar_wait(&full_bar[stage], phase);             // residual landed / slot handed over
-                const int c0 = (colq & 1) * 32;                 // first column inside the group's 64
-                const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + colq * 32);
+                if (P.dbg & 4) {                                // measurement: main loop only
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    continue;
+                }
 #pragma unroll
-                for (int cc = 0; cc < 32; cc += 16) {
+                for (int g = 0; g < 2; ++g) {
+                    const int n = nt * BN + g * 64 + csub * 16;                 // first output channel of this thread
+                    const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                          (uint32_t)(acc * 2 * BN + g * 64 + csub * 16);
                     uint32_t r0[16], r1[16];
-                    tmem_ld16(t_d0 + cc, r0);
-                    if (x3) tmem_ld16(t_d0 + BN + cc, r1);
+                    tmem_ld16(t_d0, r0);
+                    if (x3) tmem_ld16(t_d0 + BN, r1);
                     tmem_ld_wait();
+                    if (g == 1) {                               // last TMEM read of the tile: hand the accumulator back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    uint32_t oh[8], ol[8];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const int col = c0 + cc + q * 8;                               // column inside the group's 64
-                        const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((col >> 3) ^ (row & 7)) << 4);
-                        const float4 s0 = *reinterpret_cast<const float4*>(ss + col), s1 = *reinterpret_cast<const float4*>(ss + col + 4);
-                        const float4 h0 = *reinterpret_cast<const float4*>(ss + 64 + col), h1 = *reinterpret_cast<const float4*>(ss + 64 + col + 4);
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.scale + n + q * 8));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.scale + n + q * 8 + 4));
+                        const float4 h0 = __ldg(reinterpret_cast<const float4*>(P.shift + n + q * 8));
+                        const float4 h1 = __ldg(reinterpret_cast<const float4*>(P.shift + n + q * 8 + 4));
                         const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                         const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                         float v[8];
@@ -416,18 +465,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             v[k] = fmaf(a, sc[k], sh[k]);
                         }
                         if (has_res) {
-                            const uint4 h4 = lds128(stg_hi + off);
-                            const uint4 l4 = x3 ? lds128(stg_lo + off) : make_uint4(0, 0, 0, 0);
-                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
-                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
-                                v[u * 2 + 0] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
-                                v[u * 2 + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
-                            }
+                            for (int k = 0; k < 8; ++k) v[k] += rf[g][q * 8 + k];
                         }
-                        uint32_t oh[4], ol[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float a = v[u * 2], b = v[u * 2 + 1];
@@ -437,26 +477,29 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             b = fminf(b, 65504.f);
                             const __half2 h = __floats2half2_rn(a, b);
                             const float2 hf = __half22float2(h);
-                            oh[u] = *reinterpret_cast<const uint32_t*>(&h);
-                            ol[u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                            oh[q * 4 + u] = *reinterpret_cast<const uint32_t*>(&h);
+                            ol[q * 4 + u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                         }
-                        sts128(stg_hi + off, make_uint4(oh[0], oh[1], oh[2], oh[3]));
-                        sts128(stg_lo + off, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+                    }
+                    uint8_t* stg = smem + S::STG_OFF + (S::NSTG == 2 ? g * 2 * TC_BM * 128 : 0);
+                    const uint32_t stg_hi = smem_u32(stg), stg_lo = stg_hi + TC_BM * 128;
+                    if (leader) {                           // the previous stores from this buffer have read it
+                        if (S::NSTG == 2) bulk_wait_read1(); else bulk_wait_read0();
+                    }
+                    group_bar(2, 512);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        sts128(stg_hi + soff[q], make_uint4(oh[q * 4], oh[q * 4 + 1], oh[q * 4 + 2], oh[q * 4 + 3]));
+                        sts128(stg_lo + soff[q], make_uint4(ol[q * 4], ol[q * 4 + 1], ol[q * 4 + 2], ol[q * 4 + 3]));
+                    }
+                    fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA store
+                    group_bar(1, 512);                      // half tile staged
+                    if (leader) {
+                        tma_store_2d(&maps.o_hi, stg, nt * BN + g * 64, mt * TC_BM);
+                        tma_store_2d(&maps.o_lo, stg + TC_BM * 128, nt * BN + g * 64, mt * TC_BM);
+                        bulk_commit();
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA store
-                group_bar(1 + grp, 256);                // whole half tile staged (and ss no longer read)
-                if (leader) {
-                    tma_store_2d(&maps.o_hi, stg, n0g, mt * TC_BM);
-                    tma_store_2d(&maps.o_lo, stg + TC_BM * 128, n0g, mt * TC_BM);
-                    bulk_commit();
-                    bulk_wait_read0();                  // the store has read the slot
-                    mbar_arrive(&empty_bar[stage]);     // second leader's arrival returns it to the producer
-                }
-                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (leader) bulk_wait0();
@@ -681,7 +724,12 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
                 t.c_add = px * L.cin; t.w_add = (ox - px) / 2;
             }
         }
-    if (staged) return launch_tc_variant<128, 3, true>(c, maps, P, s);
+    if (staged) {
+        // one K block per tile (res2: Cin = 64): output/residual traffic is everything, two staging buffers
+        // matter more than a third ring slot
+        if (P.num_taps * P.cin_blocks == 1 && getenv("IVOSW_NO_STAGED2") == nullptr) return launch_tc_variant<128, 2, true>(c, maps, P, s);
+        return launch_tc_variant<128, 3, true>(c, maps, P, s);
+    }
     return BN == 128 ? launch_tc_variant<128, 3, false>(c, maps, P, s) : launch_tc_variant<64, 4, false>(c, maps, P, s);
 }
 

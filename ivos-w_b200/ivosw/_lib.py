@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libivosw_b200.so")
+# IVOSW_LIB: another build of the SAME library (A/B timing of kernel variants); never a different implementation
+LIB_PATH = os.environ.get("IVOSW_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libivosw_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, 1, 2, 3, 4
 CONV_SIMT_FP32, CONV_TC_FP16X3, CONV_TC_FP16X1 = 0, 1, 2
