@@ -512,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 tc_fence_after();
                 const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * COLS);
 #pragma unroll 1
-                for (int cc = 0; cc < COLS; cc += 32) {
+                for (int cc = 0; cc < ((P.dbg & 4) ? 0 : COLS); cc += 32) {
                     uint32_t r0[32], r1[32];
                     tmem_ld32(t_d0 + cc, r0);
                     if (x3) tmem_ld32(t_d0 + BN + cc, r1);
