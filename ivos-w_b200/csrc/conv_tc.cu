@@ -161,6 +161,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -320,10 +326,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
     } else if (warp == 1) {
         // ====================================== MMA issuer ======================================
-        if (lane == 0) {
+        // The whole warp walks the loop with warp-uniform values and elect.sync picks the issuing lane: descriptors
+        // and barrier addresses then live in uniform registers and every UTCHMMA / UTCBAR issues straight, without
+        // the ELECT / BRA.U.ANY waterfall ptxas wraps around per-thread operands.  tcgen05.mma issue is close to
+        // synchronous (scripts/umma_rate.cu: any result-consuming instruction between two bursts shows up as a
+        // tensor-pipe bubble), so the instruction stream between the last MMA of a block and the first of the next
+        // is kept as short as possible.
+        {
             // instruction descriptor: D = F32, A = B = F16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const bool no_mma = (P.dbg & 2) != 0;                // measurement: loads + epilogue only
+            const bool skip_res_slot = STAGED_ && P.res_hi != nullptr;
+            const uint32_t smem_base = smem_u32(smem);
             int stage = 0; uint32_t full_bits = 0;               // parity of the next operand block, per slot
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -335,33 +350,34 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     mbar_wait(&full_bar[stage], (full_bits >> stage) & 1u);
                     full_bits ^= 1u << stage;
                     tc_fence_after();
-                    const uint32_t st = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint32_t st = smem_base + (uint32_t)(stage * S::STAGE_BYTES);
                     const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + S::A_BYTES);
                     const uint64_t b_hi = make_sw128_desc(st + 2 * S::A_BYTES);
-                    const uint64_t b_lo = make_sw128_desc(st + 2 * S::A_BYTES + S::B_BYTES);
+                    if (elect_one()) {
+                        if (!no_mma) {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // +32 bytes inside the swizzle row
-                        const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-                        if (P.dbg & 2) continue;      // measurement: loads + epilogue only
-                        if (x3) {
-                            // [D0 | D1] += A_hi * [W_hi ; W_lo]^T as ONE N = 2*BN instruction (the two weight tiles are
-                            // contiguous in the stage, the two accumulators contiguous in TMEM): A_hi is read from
-                            // shared memory once instead of twice — the shared-memory port is what bounds this loop
-                            umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, accum);
-                            umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
-                        } else {
-                            umma_f16(d0, a_hi + adv, b_hi + adv, idesc, accum);
+                            for (int k = 0; k < TC_BK / 16; ++k) {
+                                const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // +32 bytes inside the swizzle row
+                                const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                                if (x3) {
+                                    // [D0 | D1] += A_hi * [W_hi ; W_lo]^T as ONE N = 2*BN instruction (the two weight
+                                    // tiles are contiguous in the stage, the two accumulators contiguous in TMEM):
+                                    // A_hi is read from shared memory once instead of twice
+                                    umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, accum);
+                                    umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+                                } else {
+                                    umma_f16(d0, a_hi + adv, b_hi + adv, idesc, accum);
+                                }
+                            }
                         }
+                        umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                        if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
                     }
-                    umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                    __syncwarp();
                     if (++stage == S::STAGES) stage = 0;
                 }
-                if constexpr (STAGED_) {
-                    if (P.res_hi != nullptr) {                   // step over the residual block's ring position
-                        if (++stage == S::STAGES) stage = 0;
-                    }
+                if (skip_res_slot) {                             // step over the residual block's ring position
+                    if (++stage == S::STAGES) stage = 0;
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -560,6 +576,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         uint4* pl = reinterpret_cast<uint4*>(P.out_lo + off);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
+                            if ((P.dbg & 32) && oh[q * 4] != 0x7fff7fffu) continue;     // measurement: compute, no stores
                             ph[q] = make_uint4(oh[q * 4], oh[q * 4 + 1], oh[q * 4 + 2], oh[q * 4 + 3]);
                             pl[q] = make_uint4(ol[q * 4], ol[q * 4 + 1], ol[q * 4 + 2], ol[q * 4 + 3]);
                         }
