@@ -700,7 +700,12 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     const int BN = L.cout >= 128 ? 128 : 64;
     const int K = L.k * L.k * L.cin;
     // the 1x1 "expand" layers (conv3 and downsample: Cout = 4 * planes) move the most output/residual bytes
-    const bool staged = (L.k == 1 && L.cout >= 256 && (residual != nullptr || L.is_downsample)) &&
+    // Epilogue through the staging buffer + TMA stores: always for the expand layers, and for every other
+    // 128-column layer with at least two waves of tiles (coalesced stores beat the per-thread 16-byte ones by
+    // 3-40 us per layer; with fewer tiles the two-pass epilogue of the last tile is a longer tail than it saves)
+    const long long n_tiles = (((long long)B * L.out_hw * L.out_hw + TC_BM - 1) / TC_BM) * (L.cout / BN);
+    const bool staged = BN == 128 &&
+                        ((L.k == 1 && L.cout >= 256 && (residual != nullptr || L.is_downsample)) || n_tiles >= 2 * c->sm_count) &&
                         getenv("IVOSW_NO_STAGED_EPILOGUE") == nullptr;
     int rc;
     TcMaps maps;
