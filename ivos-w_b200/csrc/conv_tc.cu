@@ -312,9 +312,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = smem + stage * S::STAGE_BYTES;
                         uint64_t* rb = &res_full[t_local & 1];
-                        mbar_expect_tx(rb, (x3 ? 4u : 2u) * TC_BM * 128);
+                        mbar_expect_tx(rb, (x3 ? 2u : 1u) * (BN / 64) * TC_BM * 128);
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
+                        for (int g = 0; g < BN / 64; ++g) {
                             tma_load_2d(st + g * 2 * TC_BM * 128, &maps.r_hi, rb, nt * BN + g * 64, m0);
                             if (x3) tma_load_2d(st + g * 2 * TC_BM * 128 + TC_BM * 128, &maps.r_lo, rb, nt * BN + g * 64, m0);
                         }
@@ -391,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int row = quarter * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         if constexpr (STAGED_) {
-            static_assert(!STAGED_ || BN == 128, "staged epilogue is built for 128-column tiles");
+            constexpr int NP = BN / 64;                         // passes of 64 columns per tile
             // 16 warps: quarter = TMEM lane quarter (a hardware rule: warp % 4), csub = which 16-column slice
             // of the 64-column pass this warp owns
             const int csub = e >> 2;
@@ -403,9 +403,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             uint32_t soff[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) soff[q] = (uint32_t)row * 128u + (uint32_t)(((2 * csub + q) ^ (row & 7)) << 4);
-            float rf[2][16];                                    // this thread's residual values: [pass][column]
+            float rf[NP][16];                                   // this thread's residual values: [pass][column]
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
+            for (int g = 0; g < NP; ++g)
 #pragma unroll
                 for (int k = 0; k < 16; ++k) rf[g][k] = 0.f;
             int stage = 0, t_local = 0;                         // ring position of the residual blocks
@@ -418,7 +418,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     mbar_wait(&res_full[t_local & 1], (uint32_t)(t_local >> 1) & 1u);
                     const uint32_t rs = smem_u32(smem + stage * S::STAGE_BYTES);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g)
+                    for (int g = 0; g < NP; ++g)
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const uint4 h4 = lds128(rs + g * 2 * TC_BM * 128 + soff[q]);
@@ -451,7 +451,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     continue;
                 }
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < NP; ++g) {
                     const int n = nt * BN + g * 64 + csub * 16;                 // first output channel of this thread
                     const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                           (uint32_t)(acc * 2 * BN + g * 64 + csub * 16);
@@ -459,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     tmem_ld16(t_d0, r0);
                     if (x3) tmem_ld16(t_d0 + BN, r1);
                     tmem_ld_wait();
-                    if (g == 1) {                               // last TMEM read of the tile: hand the accumulator back
+                    if (g == NP - 1) {                          // last TMEM read of the tile: hand the accumulator back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -701,11 +701,10 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     const int K = L.k * L.k * L.cin;
     // the 1x1 "expand" layers (conv3 and downsample: Cout = 4 * planes) move the most output/residual bytes
     // Epilogue through the staging buffer + TMA stores: always for the expand layers, and for every other
-    // 128-column layer with at least two waves of tiles (coalesced stores beat the per-thread 16-byte ones by
+    // layer with at least two waves of tiles (coalesced stores beat the per-thread 16-byte ones by
     // 3-40 us per layer; with fewer tiles the two-pass epilogue of the last tile is a longer tail than it saves)
     const long long n_tiles = (((long long)B * L.out_hw * L.out_hw + TC_BM - 1) / TC_BM) * (L.cout / BN);
-    const bool staged = BN == 128 &&
-                        ((L.k == 1 && L.cout >= 256 && (residual != nullptr || L.is_downsample)) || n_tiles >= 2 * c->sm_count) &&
+    const bool staged = ((L.k == 1 && L.cout >= 256 && (residual != nullptr || L.is_downsample)) || n_tiles >= 2 * c->sm_count) &&
                         getenv("IVOSW_NO_STAGED_EPILOGUE") == nullptr;
     int rc;
     TcMaps maps;
@@ -747,6 +746,7 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
             }
         }
     if (staged) {
+        if (BN == 64) return launch_tc_variant<64, 4, true>(c, maps, P, s);
         // one K block per tile (res2: Cin = 64): output/residual traffic is everything, two staging buffers
         // matter more than a third ring slot
         if (P.num_taps * P.cin_blocks == 1 && getenv("IVOSW_NO_STAGED2") == nullptr) return launch_tc_variant<128, 2, true>(c, maps, P, s);
