@@ -73,6 +73,10 @@ IVOSW_API void ivosw_destroy(ivosw_ctx* ctx);
 IVOSW_API int ivosw_set_conv_mode(ivosw_ctx* ctx, int conv_mode);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 IVOSW_API long long ivosw_launch_count(const ivosw_ctx* ctx);
+/* Host-to-device bytes the last host-buffer call (ivosw_round_host / ivosw_score_shard_host) actually sent: the
+ * background probability channel and the frame rows no ROI can touch are not transferred (bench.py's
+ * e2e.h2d_bytes_per_step). */
+IVOSW_API long long ivosw_last_h2d_bytes(const ivosw_ctx* ctx);
 
 /* ---- Q-network (models/agent.py::Brain) --------------------------------------------------
  * params_host: the 180 993 floats of Brain.state_dict() concatenated in this order

@@ -447,7 +447,8 @@ void ivosw_destroy(ivosw_ctx* c) {
     }
     DeviceBuffer* bufs[] = {&c->brain_gi, &c->brain_h, &c->brain_state, &c->brain_q, &c->brain_arg, &c->bbox_min,
                             &c->bbox_max, &c->boxes, &c->crop, &c->crop_hi, &c->crop_lo, &c->c1, &c->pool, &c->actX, &c->actY, &c->actDS,
-                            &c->actT1, &c->actT2, &c->scores, &c->scores_all, &c->mq, &c->stage_frames, &c->stage_probs};
+                            &c->actT1, &c->actT2, &c->scores, &c->scores_all, &c->mq, &c->stage_frames, &c->stage_probs, &c->band_min, &c->band_max,
+                            &c->band_rows};
     for (DeviceBuffer* b : bufs) release(*b);
     for (DeviceBuffer& b : c->probe_buf) release(b);
     for (auto& g : c->graphs) drop_graph(c, g);
@@ -459,6 +460,8 @@ void ivosw_destroy(ivosw_ctx* c) {
     for (cudaEvent_t e : c->evt_pool) cudaEventDestroy(e);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->pinned_rows) cudaFreeHost(c->pinned_rows);
     for (cudaEvent_t e : c->chunk_evts) cudaEventDestroy(e);
     delete c;
 }
@@ -471,6 +474,8 @@ int ivosw_set_conv_mode(ivosw_ctx* c, int conv_mode) {
 }
 
 long long ivosw_launch_count(const ivosw_ctx* c) { return c ? c->launches : 0; }
+
+long long ivosw_last_h2d_bytes(const ivosw_ctx* c) { return c ? c->last_h2d_bytes : 0; }
 
 int ivosw_enable_probes(ivosw_ctx* c, int enable) {
     IVOSW_REQUIRE(c != nullptr, "ctx");
@@ -695,49 +700,121 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
     const int Tl = t_end - t_begin;
     const size_t HW = (size_t)H * W;
     int rc;
-    // chunk schedule: FC frames per chunk, tapering (halving down to 4) over the last FC frames so that the
-    // compute left over after the final copy — the only part PCIe cannot hide — is small
+    // chunk schedule (frames per upload + scoring pass)
     const int FC = e2e_chunk_frames();
     std::vector<int> bounds;
-    {
-        int pos = t_begin;
-        while (t_end - pos > FC) { bounds.push_back(pos); pos += FC; }
-        int rem = t_end - pos;
-        while (rem > 0) {
-            const int take = rem > 4 ? std::max(4, rem / 2) : rem;
-            bounds.push_back(pos); pos += take; rem -= take;
+    if (const char* sch = getenv("IVOSW_E2E_SCHEDULE")) {      // measurement: explicit chunk sizes "4,12,16,..." (last repeats)
+        int pos = t_begin, last = FC;
+        const char* p = sch;
+        while (pos < t_end) {
+            if (*p) { last = std::max(1, atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+            bounds.push_back(pos); pos += std::min(last, t_end - pos);
         }
+        bounds.push_back(t_end);
+    } else {
+        // FC/2 first (the first scoring pass starts as early as possible), then FC per chunk, whatever is left
+        // (at most FC) last.  Measured on C2 (scripts/ab_e2e.sh): 8,16,16,16,8 frames = 10.6 ms against 11.6 ms for
+        // 16,16,16,8,4,4 — per-pass efficiency matters more than a short tail, the round is compute-bound once
+        // only the ROI row bands are sent.
+        int pos = t_begin;
+        const int first = std::max(1, FC / 2);
+        bounds.push_back(pos); pos += std::min(first, t_end - pos);
+        while (pos < t_end) { bounds.push_back(pos); pos += std::min(FC, t_end - pos); }
         bounds.push_back(t_end);
     }
     const int n_chunks = (int)bounds.size() - 1;
     if (!c->copy_stream) IVOSW_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    while ((int)c->chunk_evts.size() < n_chunks + 1) {
+    if (!c->aux_stream) IVOSW_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    while ((int)c->chunk_evts.size() < 3 * n_chunks + 1) {
         cudaEvent_t e;
         IVOSW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->chunk_evts.push_back(e);
     }
+    cudaEvent_t* ev_p = c->chunk_evts.data();                 // probability planes of chunk ci on the device
+    cudaEvent_t* ev_b = c->chunk_evts.data() + n_chunks;      // row ranges of chunk ci in pinned memory
+    cudaEvent_t* ev_f = c->chunk_evts.data() + 2 * n_chunks;  // frame rows of chunk ci on the device
+    cudaEvent_t ev_start = c->chunk_evts[3 * n_chunks];
     if ((rc = ensure(c->stage_frames, sizeof(float) * (size_t)T * 3 * HW))) return rc;
     if ((rc = ensure(c->stage_probs, sizeof(float) * (size_t)T * (O + 1) * HW))) return rc;
     if (keep_scores && (rc = ensure(c->scores_all, sizeof(float) * (size_t)Tl * O))) return rc;
+    if ((rc = ensure(c->band_rows, sizeof(int2) * (size_t)T))) return rc;
+    if (c->pinned_rows_n < (size_t)T) {
+        if (c->pinned_rows) cudaFreeHost(c->pinned_rows);
+        c->pinned_rows = nullptr; c->pinned_rows_n = 0;
+        IVOSW_CUDA(cudaMallocHost((void**)&c->pinned_rows, sizeof(int2) * (size_t)T));
+        c->pinned_rows_n = (size_t)T;
+    }
     float* fs = (float*)c->stage_frames.p;
     float* ps = (float*)c->stage_probs.p;
+    // Only the rows of a frame that an ROI can touch are sent (IVOSW_E2E_BANDS=0: whole frames).  Per chunk: probability
+    // planes -> pre-pass on a side stream (bbox + the sampler's own row arithmetic) -> 8 bytes per frame back to the host
+    // -> one strided copy per frame for its row band -> scoring pass.  The link idles for the ~50 us of the pre-pass
+    // round trip per chunk; queueing the next chunk's planes ahead of these rows instead delays the scoring pass by a
+    // whole plane transfer and measured slower (12.1 vs 11.6 ms).
+    const bool bands = !(getenv("IVOSW_E2E_BANDS") && atoi(getenv("IVOSW_E2E_BANDS")) == 0);
     // the copy stream must not overtake work already queued on s that may still read the staging buffers
-    IVOSW_CUDA(cudaEventRecord(c->chunk_evts[n_chunks], s));
-    IVOSW_CUDA(cudaStreamWaitEvent(c->copy_stream, c->chunk_evts[n_chunks], 0));
-    for (int ci = 0; ci < n_chunks; ++ci) {
+    IVOSW_CUDA(cudaEventRecord(ev_start, s));
+    IVOSW_CUDA(cudaStreamWaitEvent(c->copy_stream, ev_start, 0));
+    if (getenv("IVOSW_E2E_POISON") && atoi(getenv("IVOSW_E2E_POISON")) != 0)   // tests: unsent rows must never be read
+        IVOSW_CUDA(cudaMemsetAsync(fs, 0xff, sizeof(float) * (size_t)T * 3 * HW, c->copy_stream));
+    long long sent = 0;
+    auto send_probs = [&](int ci) -> int {
         const int c0 = bounds[ci], c1 = bounds[ci + 1];
-        IVOSW_CUDA(cudaMemcpyAsync(fs + (size_t)c0 * 3 * HW, frames_host + (size_t)c0 * 3 * HW,
-                                   sizeof(float) * (size_t)(c1 - c0) * 3 * HW, cudaMemcpyHostToDevice, c->copy_stream));
         IVOSW_CUDA(cudaMemcpy2DAsync(ps + ((size_t)c0 * (O + 1) + 1) * HW, sizeof(float) * (size_t)(O + 1) * HW,
                                      probs_host + ((size_t)c0 * (O + 1) + 1) * HW, sizeof(float) * (size_t)(O + 1) * HW,
                                      sizeof(float) * (size_t)O * HW, (size_t)(c1 - c0), cudaMemcpyHostToDevice,
                                      c->copy_stream));
-        IVOSW_CUDA(cudaEventRecord(c->chunk_evts[ci], c->copy_stream));
-        IVOSW_CUDA(cudaStreamWaitEvent(s, c->chunk_evts[ci], 0));
+        sent += (long long)sizeof(float) * O * HW * (c1 - c0);
+        IVOSW_CUDA(cudaEventRecord(ev_p[ci], c->copy_stream));
+        if (!bands) return IVOSW_OK;
+        int r;
+        IVOSW_CUDA(cudaStreamWaitEvent(c->aux_stream, ev_p[ci], 0));
+        UnitAddr ua{fs + (long long)c0 * 3 * (long long)HW, 3 * (long long)HW,
+                    ps + ((long long)c0 * (O + 1) + 1) * (long long)HW, (long long)(O + 1) * (long long)HW, (long long)HW,
+                    c1 - c0, 0};
+        if ((r = launch_bbox(c, ua, (c1 - c0) * O, H, W, c->aux_stream, &c->band_min, &c->band_max))) return r;
+        if ((r = launch_roi_rows(c, (const int2*)c->band_min.p, (const int2*)c->band_max.p, c1 - c0, O, H, W,
+                                 (int2*)c->band_rows.p + c0, c->aux_stream)))
+            return r;
+        IVOSW_CUDA(cudaMemcpyAsync(c->pinned_rows + c0, (int2*)c->band_rows.p + c0, sizeof(int2) * (size_t)(c1 - c0),
+                                   cudaMemcpyDeviceToHost, c->aux_stream));
+        IVOSW_CUDA(cudaEventRecord(ev_b[ci], c->aux_stream));
+        return IVOSW_OK;
+    };
+    if (bands) {      // band_min / band_max are sized once, for the largest chunk, before anything is queued on them
+        int big = 0;
+        for (int ci = 0; ci < n_chunks; ++ci) big = std::max(big, bounds[ci + 1] - bounds[ci]);
+        if ((rc = ensure(c->band_min, sizeof(int2) * (size_t)big * O))) return rc;
+        if ((rc = ensure(c->band_max, sizeof(int2) * (size_t)big * O))) return rc;
+    }
+    if ((rc = send_probs(0))) return rc;
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int c0 = bounds[ci], c1 = bounds[ci + 1];
+        if (bands) {
+            IVOSW_CUDA(cudaEventSynchronize(ev_b[ci]));
+            for (int t = c0; t < c1; ++t) {
+                const int2 r = c->pinned_rows[t];
+                if (r.x > r.y) continue;
+                const size_t off = (size_t)t * 3 * HW + (size_t)r.x * W;
+                const size_t bytes = sizeof(float) * (size_t)(r.y - r.x + 1) * W;
+                IVOSW_CUDA(cudaMemcpy2DAsync(fs + off, sizeof(float) * HW, frames_host + off, sizeof(float) * HW, bytes, 3,
+                                             cudaMemcpyHostToDevice, c->copy_stream));
+                sent += 3 * (long long)bytes;
+            }
+        } else {
+            IVOSW_CUDA(cudaMemcpyAsync(fs + (size_t)c0 * 3 * HW, frames_host + (size_t)c0 * 3 * HW,
+                                       sizeof(float) * (size_t)(c1 - c0) * 3 * HW, cudaMemcpyHostToDevice, c->copy_stream));
+            sent += (long long)sizeof(float) * 3 * HW * (c1 - c0);
+            if (ci + 1 < n_chunks && (rc = send_probs(ci + 1))) return rc;
+        }
+        IVOSW_CUDA(cudaEventRecord(ev_f[ci], c->copy_stream));
+        if (bands && ci + 1 < n_chunks && (rc = send_probs(ci + 1))) return rc;       // next planes right behind these rows
+        IVOSW_CUDA(cudaStreamWaitEvent(s, ev_f[ci], 0));
         if ((rc = score_shard(c, fs, ps, T, O, H, W, c0, c1, nullptr, mq_dev + (c0 - t_begin), nullptr,
                               keep_scores ? (float*)c->scores_all.p + (c0 - t_begin) : nullptr, Tl, s)))
             return rc;
     }
+    c->last_h2d_bytes = sent;
     return IVOSW_OK;
 }
 

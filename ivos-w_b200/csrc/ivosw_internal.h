@@ -163,6 +163,10 @@ struct ivosw_ctx {
     void* pinned_small = nullptr;    // small pinned scratch for D2H results
     size_t pinned_small_bytes = 0;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;     // row-range pre-pass of the host-buffer path
+    ivosw::DeviceBuffer band_min, band_max, band_rows;
+    int2* pinned_rows = nullptr; size_t pinned_rows_n = 0;
+    long long last_h2d_bytes = 0;          // bytes the last host-buffer call actually sent
 };
 
 namespace ivosw {
@@ -175,7 +179,9 @@ void stage_end(ivosw_ctx* c, int idx, cudaStream_t s);
 void release(DeviceBuffer& b);
 
 // ---- roi.cu
-int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s);
+int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s, DeviceBuffer* mn_buf = nullptr,
+                DeviceBuffer* mx_buf = nullptr);
+int launch_roi_rows(ivosw_ctx* c, const int2* mn, const int2* mx, int nF, int O, int H, int W, int2* rows, cudaStream_t s);
 int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, bool split,
                       cudaStream_t s);
 int launch_crop_merge(ivosw_ctx* c, float* out, int B, int use_lo, cudaStream_t s);

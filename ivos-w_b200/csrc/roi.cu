@@ -64,12 +64,15 @@ __global__ void __launch_bounds__(256) bbox_kernel(UnitAddr ua, int HW, int W, i
     }
 }
 
-int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s) {
+int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s, DeviceBuffer* mn_buf,
+                DeviceBuffer* mx_buf) {
     int rc;
-    if ((rc = ensure(c->bbox_min, sizeof(int2) * (size_t)B))) return rc;
-    if ((rc = ensure(c->bbox_max, sizeof(int2) * (size_t)B))) return rc;
-    IVOSW_CUDA(cudaMemsetAsync(c->bbox_min.p, 0x7f, sizeof(int2) * (size_t)B, s));
-    IVOSW_CUDA(cudaMemsetAsync(c->bbox_max.p, 0xff, sizeof(int2) * (size_t)B, s));
+    DeviceBuffer& bmin = mn_buf ? *mn_buf : c->bbox_min;
+    DeviceBuffer& bmax = mx_buf ? *mx_buf : c->bbox_max;
+    if ((rc = ensure(bmin, sizeof(int2) * (size_t)B))) return rc;
+    if ((rc = ensure(bmax, sizeof(int2) * (size_t)B))) return rc;
+    IVOSW_CUDA(cudaMemsetAsync(bmin.p, 0x7f, sizeof(int2) * (size_t)B, s));
+    IVOSW_CUDA(cudaMemsetAsync(bmax.p, 0xff, sizeof(int2) * (size_t)B, s));
     const int HW = H * W;
     // enough CTAs to cover the machine a few times over, each with >= 16 KB of plane
     int ctas = max(1, min((HW + 4095) / 4096, (8 * c->sm_count + B - 1) / B));
@@ -79,9 +82,9 @@ int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStrea
                (ua.obj_stride % 4 == 0) && (HW % 4 == 0);
     dim3 grid(ctas, B);
     if (vec)
-        bbox_kernel<true><<<grid, 256, 0, s>>>(ua, HW, W, per_cta, (int2*)c->bbox_min.p, (int2*)c->bbox_max.p);
+        bbox_kernel<true><<<grid, 256, 0, s>>>(ua, HW, W, per_cta, (int2*)bmin.p, (int2*)bmax.p);
     else
-        bbox_kernel<false><<<grid, 256, 0, s>>>(ua, HW, W, per_cta, (int2*)c->bbox_min.p, (int2*)c->bbox_max.p);
+        bbox_kernel<false><<<grid, 256, 0, s>>>(ua, HW, W, per_cta, (int2*)bmin.p, (int2*)bmax.p);
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
@@ -126,6 +129,53 @@ __device__ inline float lin256(int i) {
     return (i < ROI / 2) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(ROI - 1 - i), 1.0f);
 }
 
+// get_ROI_grid (:77-93), fp32 tensor arithmetic, scale = 1.0; no FMA contraction
+__device__ inline void roi_theta(const float* r, int H, int W, float* th) {
+    float rh = __fmul_rn(1.0f, r[2]), rw = __fmul_rn(1.0f, r[3]);
+    float ymin = __fsub_rn(r[0], __fdiv_rn(rh, 2.f)), ymax = __fadd_rn(r[0], __fdiv_rn(rh, 2.f));
+    float xmin = __fsub_rn(r[1], __fdiv_rn(rw, 2.f)), xmax = __fadd_rn(r[1], __fdiv_rn(rw, 2.f));
+    float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    th[0] = __fdiv_rn(__fsub_rn(xmax, xmin), wm1);                        // theta[0,0]
+    th[1] = __fdiv_rn(__fsub_rn(__fadd_rn(xmin, xmax), wm1), wm1);        // theta[0,2]
+    th[2] = __fdiv_rn(__fsub_rn(ymax, ymin), hm1);                        // theta[1,1]
+    th[3] = __fdiv_rn(__fsub_rn(__fadd_rn(ymin, ymax), hm1), hm1);        // theta[1,2]
+}
+
+// source row of ROI row oy, exactly as roi_sample_kernel evaluates it
+__device__ inline float roi_src_row(const float* th, int oy, int H) {
+    const float gy = __fadd_rn(__fmul_rn(th[2], lin256(oy)), th[3]);
+    return __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+}
+
+// Host-resident clips (capi.cu, score_range_from_host): which rows of frame t can the sampler touch?  One thread
+// per frame takes the union over the frame's objects of [floor(iy(0)), floor(iy(255)) + 1], clipped to the image,
+// with the very arithmetic of the sampler (plus one row of slack each side).  rows[t] = (first, last); first > last
+// means no row of the frame is read (every ROI row falls outside the image).
+__global__ void roi_rows_kernel(const int2* __restrict__ mn, const int2* __restrict__ mx, int nF, int O, int H, int W,
+                                int2* __restrict__ rows) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nF) return;
+    int lo = H, hi = -1;
+    for (int o = 0; o < O; ++o) {
+        const int u = o * nF + t;                      // unit order of UnitAddr: u = object * nF + frame
+        float r[4], th[4];
+        box_from_minmax(mn[u], mx[u], H, W, r);
+        roi_theta(r, H, W, th);
+        const float a = roi_src_row(th, 0, H), b = roi_src_row(th, ROI - 1, H);
+        int y0 = (int)floorf(fminf(a, b)) - 1, y1 = (int)floorf(fmaxf(a, b)) + 2;
+        y0 = max(y0, 0); y1 = min(y1, H - 1);
+        if (y0 <= y1) { lo = min(lo, y0); hi = max(hi, y1); }
+    }
+    rows[t] = make_int2(lo, hi);
+}
+
+int launch_roi_rows(ivosw_ctx* c, const int2* mn, const int2* mx, int nF, int O, int H, int W, int2* rows, cudaStream_t s) {
+    roi_rows_kernel<<<(nF + 63) / 64, 64, 0, s>>>(mn, mx, nF, O, H, W, rows);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
 constexpr int ROI_ROWS_PER_CTA = 8;
 
 // SPLIT = false: crop is [B][256][256] float4 (fp32 validation path).
@@ -146,15 +196,7 @@ __global__ void __launch_bounds__(256) roi_sample_kernel(UnitAddr ua, int H, int
         if (blockIdx.x == 0 && boxes) {
             boxes[4 * b + 0] = r[0]; boxes[4 * b + 1] = r[1]; boxes[4 * b + 2] = r[2]; boxes[4 * b + 3] = r[3];
         }
-        // get_ROI_grid (:77-93), fp32 tensor arithmetic, scale = 1.0; no FMA contraction
-        float rh = __fmul_rn(1.0f, r[2]), rw = __fmul_rn(1.0f, r[3]);
-        float ymin = __fsub_rn(r[0], __fdiv_rn(rh, 2.f)), ymax = __fadd_rn(r[0], __fdiv_rn(rh, 2.f));
-        float xmin = __fsub_rn(r[1], __fdiv_rn(rw, 2.f)), xmax = __fadd_rn(r[1], __fdiv_rn(rw, 2.f));
-        float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-        th[0] = __fdiv_rn(__fsub_rn(xmax, xmin), wm1);                        // theta[0,0]
-        th[1] = __fdiv_rn(__fsub_rn(__fadd_rn(xmin, xmax), wm1), wm1);        // theta[0,2]
-        th[2] = __fdiv_rn(__fsub_rn(ymax, ymin), hm1);                        // theta[1,1]
-        th[3] = __fdiv_rn(__fsub_rn(__fadd_rn(ymin, ymax), hm1), hm1);        // theta[1,2]
+        roi_theta(r, H, W, th);
     }
     __syncthreads();
     const int ox = threadIdx.x;
@@ -172,8 +214,7 @@ __global__ void __launch_bounds__(256) roi_sample_kernel(UnitAddr ua, int H, int
 #pragma unroll 2
     for (int r = 0; r < ROI_ROWS_PER_CTA; ++r) {
         const int oy = blockIdx.x * ROI_ROWS_PER_CTA + r;
-        const float gy = __fadd_rn(__fmul_rn(th[2], lin256(oy)), th[3]);
-        const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+        const float iy = roi_src_row(th, oy, H);
         const float fy0 = floorf(iy);
         const int y0 = (int)fy0, y1 = y0 + 1;
         const float wy1 = __fsub_rn(iy, fy0), wy0 = __fsub_rn(1.f, wy1);

@@ -26,6 +26,7 @@ SYMBOLS = {
     "ivosw_destroy": (None, [C.c_void_p]),
     "ivosw_set_conv_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "ivosw_launch_count": (C.c_longlong, [C.c_void_p]),
+    "ivosw_last_h2d_bytes": (C.c_longlong, [C.c_void_p]),
     "ivosw_brain_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ivosw_brain_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ivosw_dqn_load_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

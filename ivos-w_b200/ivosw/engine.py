@@ -227,6 +227,10 @@ class Engine:
                                      _stream(self.device)))
         return {"mask_quality": mq, "scores": sc, "q": q, "next_frame": int(nf.value) if full else None}
 
+    def last_h2d_bytes(self):
+        """Bytes the last host-buffer call actually sent to the device."""
+        return int(lib.ivosw_last_h2d_bytes(self._h))
+
     def round_host(self, all_F, all_P, annotated_counts, want_scores=False):
         """Same round from host tensors (pinned or pageable CPU fp32, contiguous)."""
         if all_F.device.type != "cpu" or all_P.device.type != "cpu":

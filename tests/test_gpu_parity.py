@@ -116,9 +116,16 @@ def test_round_vs_golden(eng, golden_dir, name):
     q64 = np.sort(g["f64_q"])[::-1]
     if T == 1 or q64[0] - q64[1] > 1e-6:
         assert r["next_frame"] == int(g["f32_next_frame"])
-    # host-buffer entry point gives the same answer
-    rh = eng.round_host(torch.from_numpy(all_F), torch.from_numpy(all_P), synth.annotated_counts(annotated, T),
-                        want_scores=True)
+    # host-buffer entry point gives the same answer; only the frame rows an ROI can touch are uploaded, so the
+    # staging buffer is poisoned with NaNs first: reading a row that was not sent would show
+    os.environ["IVOSW_E2E_POISON"] = "1"
+    try:
+        rh = eng.round_host(torch.from_numpy(all_F), torch.from_numpy(all_P), synth.annotated_counts(annotated, T),
+                            want_scores=True)
+    finally:
+        del os.environ["IVOSW_E2E_POISON"]
+    full_bytes = T * (3 + O) * H * W * 4
+    assert 0 < eng.last_h2d_bytes() <= full_bytes
     assert rh["next_frame"] == r["next_frame"]
     np.testing.assert_array_equal(rh["mask_quality"], r["mask_quality"])
     np.testing.assert_array_equal(rh["scores"], r["scores"])
@@ -160,6 +167,16 @@ def test_round_properties_full_size(eng):
     nf, q = eng.agent_action(full["mask_quality"], ann)
     assert nf == full["next_frame"]
     np.testing.assert_array_equal(q, full["q"])
+    # (5) host-buffer path at full size: chunked upload, only the ROI row bands of every frame are sent (poisoned
+    #     staging buffer: an unsent row that is read would turn the scores into NaN)
+    os.environ["IVOSW_E2E_POISON"] = "1"
+    try:
+        rh = eng.round_host(torch.from_numpy(all_F), torch.from_numpy(all_P), ann, want_scores=True)
+    finally:
+        del os.environ["IVOSW_E2E_POISON"]
+    np.testing.assert_array_equal(rh["scores"], full["scores"])
+    assert rh["next_frame"] == full["next_frame"]
+    assert eng.last_h2d_bytes() < T * (3 + O) * H * W * 4
     perm = np.random.default_rng(0).permutation(T)
     pr = eng.round_device(F_d[perm].contiguous(), P_d[perm].contiguous(), ann, want_scores=True)
     np.testing.assert_array_equal(pr["scores"], full["scores"][perm])

@@ -25,7 +25,7 @@ def built_lib():
 
 def test_header_symbols_exported(built_lib):
     hdr = open(os.path.join(REPO, "include", "ivosw_b200.h")).read()
-    declared = set(re.findall(r"IVOSW_API[^;(]*?\b(ivosw_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"IVOSW_API[^;(]*?\b(ivosw_[a-z0-9_]+)\s*\(", hdr))
     assert len(declared) >= 17
     lib = ctypes.CDLL(built_lib)
     for name in declared:
