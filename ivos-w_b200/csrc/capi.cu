@@ -810,9 +810,19 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
         IVOSW_CUDA(cudaEventRecord(ev_f[ci], c->copy_stream));
         if (bands && ci + 1 < n_chunks && (rc = send_probs(ci + 1))) return rc;       // next planes right behind these rows
         IVOSW_CUDA(cudaStreamWaitEvent(s, ev_f[ci], 0));
-        if ((rc = score_shard(c, fs, ps, T, O, H, W, c0, c1, nullptr, mq_dev + (c0 - t_begin), nullptr,
-                              keep_scores ? (float*)c->scores_all.p + (c0 - t_begin) : nullptr, Tl, s)))
-            return rc;
+        // the scoring pass of a chunk is an enqueue-only sequence over stable staging pointers: CUDA-graph replay
+        // (the ~56 launches and ~300 tensor-map encodes of a pass otherwise cost more host time than the pass runs)
+        auto enqueue = [&](cudaStream_t st) -> int {
+            return score_shard(c, fs, ps, T, O, H, W, c0, c1, nullptr, mq_dev + (c0 - t_begin), nullptr,
+                               keep_scores ? (float*)c->scores_all.p + (c0 - t_begin) : nullptr, Tl, st);
+        };
+        if (c->timing_on) {
+            if ((rc = enqueue(s))) return rc;
+        } else {
+            if ((rc = ensure(c->scores, sizeof(float) * (size_t)(c1 - c0) * O))) return rc;
+            ivosw_ctx::GraphKey key{fs, ps, mq_dev + (c0 - t_begin), T, O, H, W, c0, c1, c->conv_mode, 5, keep_scores ? 1 : 0};
+            if ((rc = run_graphed(c, key, s, enqueue))) return rc;
+        }
     }
     c->last_h2d_bytes = sent;
     return IVOSW_OK;
