@@ -697,7 +697,12 @@ static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P
 
 int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const SplitAct* residual, const SplitAct& out,
                    int B, int terms, cudaStream_t s) {
-    const int BN = L.cout >= 128 ? 128 : 64;
+    // 128-column tiles, unless they would leave more than half of the SMs without a tile (small unit batches: an 8-GPU
+    // shard, the chunks of the host-buffer path): then 64-column tiles double the CTAs at work
+    const long long m_tiles = ((long long)B * L.out_hw * L.out_hw + TC_BM - 1) / TC_BM;
+    static const int narrow_below = getenv("IVOSW_NARROW_BELOW") ? atoi(getenv("IVOSW_NARROW_BELOW")) : -1;
+    const long long narrow_limit = narrow_below >= 0 ? narrow_below : c->sm_count / 2;
+    const int BN = (L.cout >= 128 && m_tiles * (L.cout / 128) > narrow_limit) ? 128 : 64;
     const int K = L.k * L.k * L.cin;
     // the 1x1 "expand" layers (conv3 and downsample: Cout = 4 * planes) move the most output/residual bytes
     // Epilogue through the staging buffer + TMA stores: always for the expand layers, and for every other
