@@ -1,3 +1,4 @@
+[ -f ivos-w_b200/lib/libivosw_b200_old.so ] || { echo 'no libivosw_b200_old.so to compare against'; exit 1; }
 # per-kernel durations of one warm round, caches left warm (single-pass metric), for two builds of the library
 for L in old new; do
   if [ $L = old ]; then export IVOSW_LIB=$PWD/ivos-w_b200/lib/libivosw_b200_old.so; else unset IVOSW_LIB; fi
