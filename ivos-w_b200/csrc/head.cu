@@ -31,16 +31,17 @@ __global__ void __launch_bounds__(256) gap_fc_kernel(const float* __restrict__ r
 }
 
 // Same, reading r5 directly in the split-fp16 form the tensor-core path produces (x = hi + lo / 2048):
-// no fp32 copy of r5 is materialised.  One CTA per sample, 256 threads x 8 channels, 128-bit loads.
-__global__ void __launch_bounds__(256) gap_fc_split_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
-                                                           int use_lo, const float* __restrict__ fcw, float fcb,
-                                                           float* __restrict__ score) {
-    const int b = blockIdx.x, ch0 = threadIdx.x * 8;
-    const uint4* ph = reinterpret_cast<const uint4*>(hi + (long long)b * 64 * 2048 + ch0);
-    const uint4* pl = reinterpret_cast<const uint4*>(lo + (long long)b * 64 * 2048 + ch0);
+// no fp32 copy of r5 is materialised.  One CTA per sample, 1024 threads = 4 pixel groups x 256 channel octets,
+// 128-bit loads, 16 pixels per thread; the four pixel-group sums are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024) gap_fc_split_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                            int use_lo, const float* __restrict__ fcw, float fcb,
+                                                            float* __restrict__ score) {
+    const int b = blockIdx.x, oct = threadIdx.x & 255, pg = threadIdx.x >> 8, ch0 = oct * 8;
+    const uint4* ph = reinterpret_cast<const uint4*>(hi + ((long long)b * 64 + pg * 16) * 2048 + ch0);
+    const uint4* pl = reinterpret_cast<const uint4*>(lo + ((long long)b * 64 + pg * 16) * 2048 + ch0);
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int p = 0; p < 64; ++p) {
+#pragma unroll 8
+    for (int p = 0; p < 16; ++p) {
         const uint4 h4 = __ldg(ph + p * 256);
         const uint4 l4 = use_lo ? __ldg(pl + p * 256) : make_uint4(0, 0, 0, 0);
         const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
@@ -52,13 +53,22 @@ __global__ void __launch_bounds__(256) gap_fc_split_kernel(const __half* __restr
             s[2 * u + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
         }
     }
-    float part = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) part = fmaf(s[k] * (1.0f / 64.0f), __ldg(fcw + ch0 + k), part);
+    __shared__ float grp[4][256][8];
     __shared__ float red[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    for (int k = 0; k < 8; ++k) grp[pg][oct][k] = s[k];
+    __syncthreads();
+    if (pg == 0) {
+        float part = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float tot = ((grp[0][oct][k] + grp[1][oct][k]) + grp[2][oct][k]) + grp[3][oct][k];
+            part = fmaf(tot * (1.0f / 64.0f), __ldg(fcw + ch0 + k), part);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(256) gap_fc_split_kernel(const __half* __restr
 }
 
 int launch_gap_fc_split(ivosw_ctx* c, const SplitAct& r5, int use_lo, int B, float* scores, cudaStream_t s) {
-    gap_fc_split_kernel<<<B, 256, 0, s>>>(r5.hi, r5.lo, use_lo, c->fc_w, c->fc_b, scores);
+    gap_fc_split_kernel<<<B, 1024, 0, s>>>(r5.hi, r5.lo, use_lo, c->fc_w, c->fc_b, scores);
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;

@@ -26,19 +26,30 @@ __global__ void __launch_bounds__(256) bbox_kernel(UnitAddr ua, int HW, int W, i
     int ymin = 0x7fffffff, xmin = 0x7fffffff, ymax = -1, xmax = -1;
     if (VEC4) {
         // start / per_cta are multiples of 4 and the plane is 16-byte aligned
-        for (int i = start + threadIdx.x * 4; i < end; i += blockDim.x * 4) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(plane + i));
-            bool any = (v.x > 0.5f) | (v.y > 0.5f) | (v.z > 0.5f) | (v.w > 0.5f);
-            if (any) {
-                float vv[4] = {v.x, v.y, v.z, v.w};
-                int y = i / W, x = i - y * W;
+        // four independent 16-byte loads in flight per thread
+        for (int i0 = start + threadIdx.x * 4; i0 < end; i0 += blockDim.x * 16) {
+            float4 v4[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (vv[j] > 0.5f) {  // strict: (tp > 0.5) then >= 0.49 on {0,1}  (SURVEY A.Q2)
-                        ymin = min(ymin, y); ymax = max(ymax, y);
-                        xmin = min(xmin, x); xmax = max(xmax, x);
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * (int)blockDim.x * 4;
+                v4[u] = i < end ? __ldg(reinterpret_cast<const float4*>(plane + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 v = v4[u];
+                const int i = i0 + u * (int)blockDim.x * 4;
+                bool any = (v.x > 0.5f) | (v.y > 0.5f) | (v.z > 0.5f) | (v.w > 0.5f);
+                if (any) {
+                    float vv[4] = {v.x, v.y, v.z, v.w};
+                    int y = i / W, x = i - y * W;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (vv[j] > 0.5f) {  // strict: (tp > 0.5) then >= 0.49 on {0,1}  (SURVEY A.Q2)
+                            ymin = min(ymin, y); ymax = max(ymax, y);
+                            xmin = min(xmin, x); xmax = max(xmax, x);
+                        }
+                        if (++x == W) { x = 0; ++y; }
                     }
-                    if (++x == W) { x = 0; ++y; }
                 }
             }
         }
