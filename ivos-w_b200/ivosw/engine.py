@@ -4,6 +4,7 @@ PyTorch is used here only for device memory, streams and (in ``dist.py``)
 ``torch.distributed``; all arithmetic happens in the CUDA library.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -12,7 +13,8 @@ from . import arch
 from ._lib import (BRAIN_NUM_PARAMS, CONV_SIMT_FP32, CONV_TC_FP16X1, CONV_TC_FP16X3, check, lib)
 
 CONV_MODES = {"simt_fp32": CONV_SIMT_FP32, "tc_fp16x3": CONV_TC_FP16X3, "tc_fp16x1": CONV_TC_FP16X1}
-DEFAULT_CONV_MODE = "tc_fp16x3"
+# arithmetic of the encoder unless a caller says otherwise (README.md, "Environment switches")
+DEFAULT_CONV_MODE = os.environ.get("IVOSW_CONV_MODE", "tc_fp16x3")
 
 
 def pack_brain(sd):
