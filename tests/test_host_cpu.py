@@ -35,6 +35,17 @@ def test_header_symbols_exported(built_lib):
     assert _lib.lib.ivosw_abi_version() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++ or torch types in the signatures) and a C
+    program must link against the library through it."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ivosw_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %s\\n", ivosw_abi_version(), ivosw_last_error()); return 0; }\n')
+    inc = os.path.join(REPO, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                   check=True)
+
+
 def test_sass_is_sm100a(built_lib):
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out
