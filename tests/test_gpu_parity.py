@@ -220,6 +220,30 @@ def test_multi_chunk_invariance():
         assert r["next_frame"] == res[0]["next_frame"]
 
 
+def test_odd_frame_size_vs_oracle(eng):
+    """Odd H, W (H*W not a multiple of 4): the scalar bbox path, unaligned plane starts and odd row pitches in the
+    strided host uploads.  Device-resident and host-buffer rounds against the CPU oracle."""
+    from oracle import round_ref
+    T, H, W, O = 3, 201, 303, 2
+    all_F, all_P, annotated = synth.make_clip(17, T, H, W, O)
+    assess_sd, brain_sd = synth.assess_state_dict(0), synth.brain_state_dict(0)
+    eng.load_assess(assess_sd)
+    eng.load_brain(brain_sd)
+    ref = round_ref.recommend_frame_wild_ours(assess_sd, brain_sd, all_F, all_P, annotated)
+    ann = synth.annotated_counts(annotated, T)
+    r = eng.round_device(torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda(), ann, want_scores=True)
+    np.testing.assert_allclose(r["scores"], ref["scores"], atol=1e-4)
+    np.testing.assert_allclose(r["q"], ref["q"], atol=1e-5)
+    assert r["next_frame"] == ref["next_frame"]
+    os.environ["IVOSW_E2E_POISON"] = "1"
+    try:
+        rh = eng.round_host(torch.from_numpy(all_F), torch.from_numpy(all_P), ann, want_scores=True)
+    finally:
+        del os.environ["IVOSW_E2E_POISON"]
+    np.testing.assert_array_equal(rh["scores"], r["scores"])
+    assert rh["next_frame"] == r["next_frame"]
+
+
 def test_out_of_memory_surfaces_as_runtime_error(eng):
     """eval_agent_manet.py:391-396 retries on RuntimeError containing 'out of memory'."""
     B = 30000                                    # ~22 MB of workspace per unit -> far beyond 180 GB
