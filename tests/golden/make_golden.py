@@ -272,6 +272,74 @@ def golden_dqn(ref_agent):
     print("dqn_step.npz: loss f32", out["f32_loss0"], out["f32_loss1"], "f64", out["f64_loss0"], out["f64_loss1"])
 
 
+TRAIN_KEYS = ("fc1.weight", "fc1.bias", "Encoder.conv1.weight", "Encoder.conv1_p.weight", "Encoder.bn1.weight",
+              "Encoder.bn1.bias", "Encoder.res2.0.conv1.weight", "Encoder.res2.0.downsample.0.weight",
+              "Encoder.res3.1.conv2.weight", "Encoder.res3.1.bn2.weight", "Encoder.res4.3.conv3.weight",
+              "Encoder.res5.2.conv3.weight", "Encoder.res5.2.bn3.bias")
+TRAIN_BUFFERS = ("Encoder.bn1.running_mean", "Encoder.bn1.running_var", "Encoder.bn1.num_batches_tracked",
+                 "Encoder.res3.1.bn2.running_mean", "Encoder.res5.2.bn3.running_var")
+TRAIN_HP = dict(lr=5e-6, momentum=0.9, weight_decay=5e-4)        # config.yaml:25-28
+
+
+def synth_train_batch(step, N=4, H=160, W=256):
+    """imgs N x 3 x H x W, probs N x H x W (object 1 of a synthetic clip), targets U[0,1] standing in for the J&F
+    metric (davisinteractive is not installed), valid[n] standing in for `union[n] > 0` (one sample skipped)."""
+    all_F, all_P, _ = synth.make_clip(40 + step, N, H, W, 1)
+    rng = np.random.default_rng(7000 + step)
+    targets = rng.random(N).astype(np.float32)
+    valid = np.ones(N, dtype=bool)
+    valid[(step + 2) % N] = False
+    return all_F, all_P[:, 1], targets, valid
+
+
+def train_state_dict():
+    """synth.assess_state_dict(0) with fc1.weight scaled by 1e-3: most encoder gradients then stay inside the
+    [-1, 1] clamp (their fp32 round-off, amplified by 53 layers of train-mode BatchNorm, is ~1e-3 relative — clamped
+    values would hide everything but the sign), while the fc1 gradients still exceed it and exercise the clamp."""
+    sd = synth.assess_state_dict(0)
+    sd["fc1.weight"] = sd["fc1.weight"] * 1e-3
+    return sd
+
+
+def golden_assess_train(ref_assess):
+    """Two consecutive iterations of quality_assessment.py::train's loop body (:240-269) with the reference's own
+    AssessNet in train mode and torch.optim.SGD — no zero_grad between them, exactly like the loop."""
+    import torch.nn.functional as F
+    out = {}
+    net = ref_assess.AssessNet()
+    net.load_state_dict(train_state_dict(), strict=True)
+    net.train()                                                              # :213
+    opt = torch.optim.SGD(net.parameters(), **TRAIN_HP)                      # :309-310
+    params = dict(net.named_parameters())
+    for step in range(2):
+        imgs, probs, targets, valid = synth_train_batch(step)
+        iou_pred = net(torch.from_numpy(imgs), torch.from_numpy(probs))      # :240
+        metric_gt = torch.from_numpy(targets)
+        loss, counter = 0., 0
+        for n in range(imgs.shape[0]):                                       # :251-257
+            if valid[n]:
+                loss += F.mse_loss(iou_pred[n], metric_gt[n])
+                counter += 1
+        loss /= counter
+        loss.backward()                                                      # :265
+        for param in net.parameters():                                       # :266-268
+            if param.grad is not None:
+                param.grad.data.clamp_(-1, 1)
+        opt.step()                                                           # :269
+        out["pred%d" % step] = iou_pred.detach().numpy().reshape(-1)
+        out["loss%d" % step] = np.float64(loss.item())
+        for k in TRAIN_KEYS:
+            stride = 101 if params[k].numel() > 10000 else 1         # fixtures kept small
+            out["grad%d_%s" % (step, k)] = params[k].grad.detach().numpy().reshape(-1)[::stride].copy()
+            out["param%d_%s" % (step, k)] = params[k].detach().numpy().reshape(-1)[::stride].copy()
+    sd = net.state_dict()
+    for k in TRAIN_BUFFERS:
+        out["buf_" + k] = sd[k].numpy().reshape(-1).copy()
+    out["no_grad_params"] = np.array(sorted(k for k, v in params.items() if v.grad is None))
+    np.savez_compressed(os.path.join(HERE, "assess_train.npz"), **out)
+    print("assess_train.npz: loss", out["loss0"], out["loss1"], "params without grad:", list(out["no_grad_params"]))
+
+
 if __name__ == "__main__":
     ref_assess, ref_agent, ref_glue = load_reference()
     with torch.no_grad():
@@ -283,3 +351,4 @@ if __name__ == "__main__":
         golden_round("round_t16", 4, 16, 128, 224, 2, "manet", ref_assess, ref_agent, ref_glue)
         golden_manet_tail()
     golden_dqn(ref_agent)
+    golden_assess_train(ref_assess)
