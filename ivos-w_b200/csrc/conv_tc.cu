@@ -20,10 +20,12 @@
 // block); each step lands A_hi/A_lo (128 x 64 fp16, 128B-swizzled, K-major) and W_hi/W_lo
 // (BN x 64) in one pipeline stage.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 =
-// epilogue (two warps per TMEM lane quarter, each taking half of the tile's columns).  Persistent
-// CTAs walk the (m-tile, n-tile) list; TMEM holds two accumulator stages so the epilogue of tile i
-// overlaps the MMAs of tile i+1.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (the whole warp walks the loop,
+// elect.sync issues), then the epilogue warps: 16 in the staged variants (output through a shared-memory
+// staging buffer and TMA stores; used wherever a layer has at least two waves of tiles), 8 in the direct
+// variant (per-thread 16-byte stores; the few-tile res5 layers).  Persistent CTAs walk the (m-tile,
+// n-tile) list n-fastest; TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs
+// of tile i+1.  Measurements behind these choices: DESIGN.md 4.3, profiles/r1_tc_ceiling.md.
 #include <cuda.h>
 
 #include "ivosw_internal.h"
