@@ -2,12 +2,15 @@
 //   bbox_kernel        tm = (tp > 0.5); per-plane min/max row/col        (:165, all2yxhw :115-125)
 //   roi_sample_kernel  all2yxhw box arithmetic (:128-157), theta (:77-93), forward affine grid
 //                      (:104-105), bilinear zero-padded sampling of RGB and prob (:173-174) and the
-//                      encoder's input normalisation (:47), written as one 4-channel NHWC crop.
+//                      encoder's input normalisation (:47), written as one 4-channel NHWC crop — for the
+//                      tensor-core stem as split-fp16 planes on a zero-bordered canvas (stem_tc.cu reads its
+//                      MMA operand straight from the canvas rows), for the fp32 validation path as float4.
+//   roi_rows_kernel    host-buffer path: which rows of a frame any of its ROIs can touch (capi.cu uploads only those)
 // The reference does the bbox on the host with numpy after a device->host copy of the mask and
 // also builds an inverse grid nobody reads (:95-107); both are dropped here (SURVEY A.Q4).
 //
 // HBM-bound.  Algorithmic bytes per (frame, object): H*W*4 read by bbox_kernel; the ROI footprint
-// of 4 planes read (<= 4*H*W*4) + 4*256*256*4 written by roi_sample_kernel.
+// of 4 planes read (<= 4*H*W*4) + 2*262*264*8 (split canvas) or 4*256*256*4 written by roi_sample_kernel.
 #include "ivosw_internal.h"
 
 namespace ivosw {
