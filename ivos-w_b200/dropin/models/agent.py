@@ -57,60 +57,56 @@ class Brain(nn.Module):
         return engine.brain_forward(input, want_argmax=True)
 
 
+# attribute <- cfg.agent field: the public attributes of the reference's Agent (agent.py:71-80)
+_AGENT_CFG = (("memory_size", "memory_size"), ("GAMMA", "gamma"), ("EPS_START", "eps_start"), ("EPS_END", "eps_end"),
+              ("EPS_DECAY", "eps_decay"), ("update_rate", "update_rate"))
+_LOSS_WINDOW = 32            # running mean of the last 32 update losses (agent.py:94-101, 198-207)
+
+
 class Agent(nn.Module):
     def __init__(self, device, cfg):
-        super(Agent, self).__init__()
-        self.cfg = cfg
-        self.device = device
-        self.memory_size = self.cfg.agent.memory_size
-        self.GAMMA = self.cfg.agent.gamma
-        self.EPS_START = self.cfg.agent.eps_start
-        self.EPS_END = self.cfg.agent.eps_end
-        self.EPS_DECAY = self.cfg.agent.eps_decay
+        super().__init__()
+        self.cfg, self.device = cfg, device
+        for attr, field in _AGENT_CFG:
+            setattr(self, attr, getattr(cfg.agent, field))
+        self.subset = cfg.data.subset
         self.steps_done = 0
-        self.update_rate = self.cfg.agent.update_rate
-        self.subset = self.cfg.data.subset
         from models.momory_pool import ReplayMemory
         self.memory_pool = ReplayMemory(self.memory_size)
 
-        self.policy_net = Brain()
-        self.target_net = Brain()
+        # two Q-networks with identical initial weights, both on `device` (agent.py:84-91)
+        self.policy_net, self.target_net = Brain(), Brain()
         self.target_net.load_state_dict(self.policy_net.state_dict())
-        self.policy_net.to(self.device)
-        self.target_net.to(self.device)
+        for net in (self.policy_net, self.target_net):
+            net.to(device)
 
-        self.loss = []
-        self.loss_position = 0
-        self.loss_capacity = 32
-        self.loss_avg = 0
+        self.loss, self.loss_position, self.loss_capacity, self.loss_avg = [], 0, _LOSS_WINDOW, 0
         self.optimizer = optim.Adam(self.policy_net.parameters(), lr=cfg.agent.lr,
                                     weight_decay=cfg.agent.weight_decay)
+
+    def _epsilon(self):
+        """Exploration threshold: 0 outside training, else an exponential decay in steps_done (agent.py:171-175)."""
+        if self.cfg.phase != 'train':
+            return 0
+        return self.EPS_END + (self.EPS_START - self.EPS_END) * math.exp(-0.5 * self.steps_done / self.EPS_DECAY)
 
     def action(self, state, verbose=True):
         """agent.py:168-196.  Side effects kept: steps_done += 1 and exactly one random.random()
         draw per call (SURVEY A.Q6) so the global RNG stream stays aligned with the reference."""
         self.steps_done += 1
-        if not self.cfg.phase == 'train':
-            eps_threshold = 0
-        else:
-            eps_threshold = self.EPS_END + (self.EPS_START - self.EPS_END) * \
-                math.exp(-0.5 * self.steps_done / self.EPS_DECAY)
+        eps_threshold = self._epsilon()
         state = np.asarray(state)
         rand_flag = random.random()
-        if rand_flag > eps_threshold:
-            if verbose:
-                print(f"step:{self.steps_done}, rand_flag:{rand_flag:.4f}, eps_threshold:{eps_threshold:.4f}, "
-                      f"frame index was selected by agent")
-            engine = get_engine(self.device)
-            self.policy_net._sync(engine)
-            action, _ = engine.agent_action(state[:, 0], state[:, 1])
-            return np.int64(action)
-        else:
-            if verbose:
-                print(f"step:{self.steps_done}, rand_flag:{rand_flag:.4f}, eps_threshold:{eps_threshold:.4f}, "
-                      f"frame index was selected randomly")
-            action_idx = np.array(range(state.shape[0]))
-            return random.choice(action_idx)
+        greedy = rand_flag > eps_threshold
+        if verbose:
+            print(f"step:{self.steps_done}, rand_flag:{rand_flag:.4f}, eps_threshold:{eps_threshold:.4f}, "
+                  f"frame index was selected {'by agent' if greedy else 'randomly'}")
+        if not greedy:
+            return random.choice(np.array(range(state.shape[0])))
+        engine = get_engine(self.device)
+        self.policy_net._sync(engine)
+        action, _ = engine.agent_action(state[:, 0], state[:, 1])
+        return np.int64(action)
 
     def _sync_target(self, engine):
         sd = self.target_net.state_dict()
@@ -154,19 +150,21 @@ class Agent(nn.Module):
         return loss
 
     def _update_avg_loss(self, loss):
+        """Ring buffer of the last `loss_capacity` losses and their mean (agent.py:198-207)."""
         if len(self.loss) < self.loss_capacity:
-            self.loss.append(None)
-        self.loss[self.loss_position] = float(loss)
+            self.loss.append(float(loss))
+        else:
+            self.loss[self.loss_position] = float(loss)
         self.loss_position = (self.loss_position + 1) % self.loss_capacity
         self.loss_avg = sum(self.loss) / len(self.loss)
 
     def set_train(self):
-        self.policy_net.train()
-        self.target_net.train()
+        for net in (self.policy_net, self.target_net):
+            net.train()
 
     def set_eval(self):
-        self.policy_net.eval()
-        self.target_net.eval()
+        for net in (self.policy_net, self.target_net):
+            net.eval()
 
     def memory(self, *args):
         self.memory_pool.push(*args[:-1])
