@@ -300,6 +300,10 @@ def run_ours(args):
                 "kernel": "conv stack res2..res5 (%s), %d launches/step, avg %.1f us/launch" %
                           (args.conv_mode, n_conv // max(1, args.steps), 1e3 * stage_ms["conv_stack"] / max(1, n_conv)),
                 "peak_source": pk["which"],
+                # achieved / frac count ALGORITHMIC flops; the fp32-grade split-fp16 mode issues three MMA terms per
+                # product, so the tensor pipe executes 3x that (what ncu's tensor-pipe % sees)
+                "mma_terms": {"tc_fp16x3": 3, "tc_fp16x1": 1}.get(args.conv_mode),
+                "executed_frac": ({"tc_fp16x3": 3, "tc_fp16x1": 1}.get(args.conv_mode, 0) * achieved / pk["tflops"]) or None,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
