@@ -103,6 +103,12 @@ IVOSW_API int ivosw_brain_forward(ivosw_ctx* ctx, const float* state_dev, int N,
 IVOSW_API int ivosw_dqn_load_target(ivosw_ctx* ctx, const float* params_host, size_t n_floats);
 IVOSW_API int ivosw_dqn_sync_target(ivosw_ctx* ctx, void* stream);
 IVOSW_API int ivosw_dqn_reset_optimizer(ivosw_ctx* ctx);
+/* Adam state for checkpoints (models/agent.py:101 optimizer; the reference's torch.optim.Adam.state_dict()):
+ * exp_avg / exp_avg_sq as 180 993 floats in blob order (device memory) and the step count.  Loading new policy
+ * weights from the host (ivosw_brain_load) resets this state; ivosw_dqn_set_optimizer restores it afterwards. */
+IVOSW_API int ivosw_dqn_get_optimizer(ivosw_ctx* ctx, float* m_dev, float* v_dev, long long* step_out, void* stream);
+IVOSW_API int ivosw_dqn_set_optimizer(ivosw_ctx* ctx, const float* m_dev, const float* v_dev, long long step,
+                                      void* stream);
 IVOSW_API int ivosw_dqn_update(ivosw_ctx* ctx, const float* state_dev, const float* new_state_dev,
                      const int* action_dev, const float* reward_step_dev, const float* reward_done_dev,
                      int N, int T, float gamma, float lr, float weight_decay, float* loss_host,
@@ -195,6 +201,13 @@ IVOSW_API int ivosw_agent_action_dev(ivosw_ctx* ctx, const double* mq_dev, const
  * chunk; ivosw_stage_times synchronises them and returns the accumulated milliseconds since the
  * last reset: [0] bbox+ROI crop, [1] stem conv+maxpool, [2] res2..res5 conv stack, [3] pool+FC,
  * [4] Brain (3 launches), and the number of conv-stack launches in n_conv_launches. */
+/* ---- fp16 range guard of the split-fp16 encoder ------------------------------------------------
+ * Activations are carried as two fp16 planes; a value beyond +-65504 is clamped.  The epilogues count
+ * the (thread, tile) pairs in which that happened; this call synchronises `stream`, returns the count
+ * since the last reset and, when it is non-zero, leaves a warning in ivosw_last_error().  0 for every
+ * network whose activations stay inside the fp16 range (the reference's trained weights: O(1..100)). */
+IVOSW_API int ivosw_conv_saturation_count(ivosw_ctx* ctx, long long* count_out, int reset, void* stream);
+
 #define IVOSW_NUM_STAGES 5
 IVOSW_API int ivosw_stage_timing(ivosw_ctx* ctx, int enable);
 IVOSW_API int ivosw_stage_times(ivosw_ctx* ctx, float* ms_out /*[IVOSW_NUM_STAGES]*/, long long* n_conv_launches,
@@ -221,6 +234,21 @@ IVOSW_API int ivosw_manet_tail(ivosw_ctx* ctx, const float* logits_dev, int T, i
  * IVOSW_ERR_INVALID if an image has no such pixel (the reference raises there). */
 IVOSW_API int ivosw_rough_roi(ivosw_ctx* ctx, const float* labels_dev, float* out_dev, int B, int h, int w,
                     int dist, void* stream);
+
+/* ---- ATNet round wrapper glue (utils/utils_atnet.py::run_VOS_singleiact; config C3) -------------
+ * The ATNet networks are external (yuk6heo/IVOS-ATNet, not in the reference tree); these are the wrapper's own
+ * element-wise passes, each one kernel:
+ *   reflect_pad    :95-96   torch.nn.ReflectionPad2d((left, right, top, bottom)) on `planes` h x w planes
+ *   sigmoid_blend  :101-102,124-126,146-150  prob = sigmoid(logit); blended = alpha*prob + one_minus_alpha*prev
+ *                  (prev_dev NULL: blended = prob, the annotated frame); blended_dev may alias prev_dev
+ *   assemble       :157-159 all_P[T][O+1][H][W]: channel 0 zero, channels 1..O = prob_map[T][O][PH][PW] cropped at
+ *                  (y0, x0) — the contiguous equivalent of cat([zeros, prob_map], 1)[:, :, hpad1:-hpad2, wpad1:-wpad2] */
+IVOSW_API int ivosw_atnet_reflect_pad(ivosw_ctx* ctx, const float* in_dev, float* out_dev, int planes, int h, int w,
+                                      int left, int right, int top, int bottom, void* stream);
+IVOSW_API int ivosw_atnet_sigmoid_blend(ivosw_ctx* ctx, const float* logit_dev, const float* prev_dev, float* prob_dev,
+                                        float* blended_dev, long long n, float alpha, float one_minus_alpha, void* stream);
+IVOSW_API int ivosw_atnet_assemble(ivosw_ctx* ctx, const float* prob_map_dev, float* all_p_dev, int T, int O, int PH, int PW,
+                                   int y0, int x0, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -314,7 +314,11 @@ int ensure_pinned(ivosw_ctx* c, size_t bytes) {
     return IVOSW_OK;
 }
 
-static bool same_key(const ivosw_ctx::GraphKey& a, const ivosw_ctx::GraphKey& b) { return memcmp(&a, &b, sizeof a) == 0; }
+// field by field: the struct has tail padding, which brace-initialised stack keys leave indeterminate
+static bool same_key(const ivosw_ctx::GraphKey& a, const ivosw_ctx::GraphKey& b) {
+    return a.p0 == b.p0 && a.p1 == b.p1 && a.p2 == b.p2 && a.T == b.T && a.O == b.O && a.H == b.H && a.W == b.W &&
+           a.tb == b.tb && a.te == b.te && a.mode == b.mode && a.kind == b.kind && a.flags == b.flags;
+}
 
 static void drop_graph(ivosw_ctx* c, ivosw_ctx::GraphEntry& e) {
     if (c->last_graph == &e) drain_graph_events(c);
@@ -345,7 +349,7 @@ static int run_graphed(ivosw_ctx* c, ivosw_ctx::GraphKey key, cudaStream_t s, F&
     }
     if (e->seen == 0) {
         const int rc = fn(s);
-        e->seen = 1; e->epoch = g_alloc_epoch;
+        if (rc == IVOSW_OK) { e->seen = 1; e->epoch = g_alloc_epoch; }    // a failed eager run is not a template for capture
         return rc;
     }
     if (!e->exec) {
@@ -416,6 +420,11 @@ int ivosw_create(int device, int conv_mode, ivosw_ctx** out) {
     c->chunk_cap = chunk_cap_default();
     { const char* g = getenv("IVOSW_GRAPHS"); c->graphs_on = !(g && atoi(g) == 0); }
     c->layers = make_resnet50_layers();
+    if (cudaMalloc(&c->sat_count, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(c->sat_count, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(cudaGetLastError(), "saturation counter", __FILE__, __LINE__);
+    }
     *out = c;
     return IVOSW_OK;
 }
@@ -433,6 +442,7 @@ void ivosw_destroy(ivosw_ctx* c) {
     if (c->adam_m) cudaFree(c->adam_m);
     if (c->adam_v) cudaFree(c->adam_v);
     release(c->dqn_ws);
+    if (c->sat_count) cudaFree(c->sat_count);
     if (c->stem_w) cudaFree(c->stem_w);
     if (c->stem_scale) cudaFree(c->stem_scale);
     if (c->stem_shift) cudaFree(c->stem_shift);
@@ -492,6 +502,14 @@ int ivosw_brain_load(ivosw_ctx* c, const float* params_host, size_t n_floats) {
     if ((rc = upload(&c->brain_params, params_host, n_floats))) return rc;
     if ((rc = brain_pack(c))) return rc;
     c->brain_loaded = true;
+    // new policy weights from the host (a fresh Agent, load_state_dict): the Adam moments and step count belonged to the
+    // previous weights.  Drop-in callers that only re-sync what the library itself produced do not come through here
+    // (dropin/models/agent.py refreshes its stamp after update_agent).
+    if (c->adam_m) {
+        IVOSW_CUDA(cudaMemset(c->adam_m, 0, sizeof(float) * IVOSW_BRAIN_NUM_PARAMS));
+        IVOSW_CUDA(cudaMemset(c->adam_v, 0, sizeof(float) * IVOSW_BRAIN_NUM_PARAMS));
+    }
+    c->adam_step = 0;
     return IVOSW_OK;
 }
 
@@ -1024,6 +1042,56 @@ int ivosw_agent_action_dev(ivosw_ctx* c, const double* mq_dev, const double* ann
     return IVOSW_OK;
 }
 
+int ivosw_conv_saturation_count(ivosw_ctx* c, long long* count_out, int reset, void* stream) {
+    IVOSW_REQUIRE(c && count_out, "null pointer");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure_pinned(c, 64))) return rc;
+    IVOSW_CUDA(cudaMemcpyAsync(c->pinned_small, c->sat_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (reset) IVOSW_CUDA(cudaMemsetAsync(c->sat_count, 0, sizeof(unsigned long long), s));
+    IVOSW_CUDA(cudaStreamSynchronize(s));
+    *count_out = (long long)*(unsigned long long*)c->pinned_small;
+    if (*count_out > 0) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "warning: %lld epilogue tiles clamped activations to the fp16 range (+-65504) in the "
+                 "split-fp16 encoder; results are outside the parity guarantee", *count_out);
+        set_error(buf);
+    }
+    return IVOSW_OK;
+}
+
+int ivosw_dqn_get_optimizer(ivosw_ctx* c, float* m_dev, float* v_dev, long long* step_out, void* stream) {
+    IVOSW_REQUIRE(c && m_dev && v_dev && step_out, "null pointer");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nb = sizeof(float) * IVOSW_BRAIN_NUM_PARAMS;
+    if (c->adam_m) {
+        IVOSW_CUDA(cudaMemcpyAsync(m_dev, c->adam_m, nb, cudaMemcpyDeviceToDevice, s));
+        IVOSW_CUDA(cudaMemcpyAsync(v_dev, c->adam_v, nb, cudaMemcpyDeviceToDevice, s));
+    } else {
+        IVOSW_CUDA(cudaMemsetAsync(m_dev, 0, nb, s));
+        IVOSW_CUDA(cudaMemsetAsync(v_dev, 0, nb, s));
+    }
+    *step_out = c->adam_step;
+    return IVOSW_OK;
+}
+
+int ivosw_dqn_set_optimizer(ivosw_ctx* c, const float* m_dev, const float* v_dev, long long step, void* stream) {
+    IVOSW_REQUIRE(c && m_dev && v_dev && step >= 0, "null pointer / negative step");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nb = sizeof(float) * IVOSW_BRAIN_NUM_PARAMS;
+    if (!c->adam_m) {
+        IVOSW_CUDA(cudaMalloc(&c->adam_m, nb));
+        IVOSW_CUDA(cudaMalloc(&c->adam_v, nb));
+    }
+    IVOSW_CUDA(cudaMemcpyAsync(c->adam_m, m_dev, nb, cudaMemcpyDeviceToDevice, s));
+    IVOSW_CUDA(cudaMemcpyAsync(c->adam_v, v_dev, nb, cudaMemcpyDeviceToDevice, s));
+    c->adam_step = step;
+    return IVOSW_OK;
+}
+
 int ivosw_stage_timing(ivosw_ctx* c, int enable) {
     IVOSW_REQUIRE(c != nullptr, "ctx");
     c->timing_on = enable != 0;
@@ -1104,6 +1172,36 @@ int ivosw_rough_roi(ivosw_ctx* c, const float* labels_dev, float* out_dev, int B
         return IVOSW_ERR_INVALID;
     }
     return IVOSW_OK;
+}
+
+// -------------------------------------------------------------------------------------- ATNet glue
+int ivosw_atnet_reflect_pad(ivosw_ctx* c, const float* in_dev, float* out_dev, int planes, int h, int w, int left, int right,
+                            int top, int bottom, void* stream) {
+    IVOSW_REQUIRE(c && in_dev && out_dev, "null pointer");
+    IVOSW_REQUIRE(planes >= 1 && planes <= 65535 && h >= 1 && w >= 1, "planes, h, w");
+    // torch.nn.ReflectionPad2d: "Padding size should be less than the corresponding input dimension"
+    IVOSW_REQUIRE(left >= 0 && right >= 0 && top >= 0 && bottom >= 0 && left < w && right < w && top < h && bottom < h,
+                  "padding must be non-negative and smaller than the input dimension");
+    IVOSW_REQUIRE(h + top + bottom <= 65535, "padded height <= 65535");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return launch_reflect_pad(c, in_dev, out_dev, planes, h, w, left, right, top, bottom, (cudaStream_t)stream);
+}
+
+int ivosw_atnet_sigmoid_blend(ivosw_ctx* c, const float* logit_dev, const float* prev_dev, float* prob_dev, float* blended_dev,
+                              long long n, float alpha, float one_minus_alpha, void* stream) {
+    IVOSW_REQUIRE(c && logit_dev && prob_dev && blended_dev, "null pointer");
+    IVOSW_REQUIRE(n >= 1 && n < (1ll << 40), "n");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return launch_sigmoid_blend(c, logit_dev, prev_dev, prob_dev, blended_dev, n, alpha, one_minus_alpha, (cudaStream_t)stream);
+}
+
+int ivosw_atnet_assemble(ivosw_ctx* c, const float* prob_map_dev, float* all_p_dev, int T, int O, int PH, int PW, int y0, int x0,
+                         int H, int W, void* stream) {
+    IVOSW_REQUIRE(c && prob_map_dev && all_p_dev, "null pointer");
+    IVOSW_REQUIRE(T >= 1 && O >= 1 && H >= 1 && W >= 1 && y0 >= 0 && x0 >= 0 && y0 + H <= PH && x0 + W <= PW, "geometry");
+    IVOSW_REQUIRE((long long)T * (O + 1) <= 65535 && H <= 65535, "T*(O+1), H <= 65535");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return launch_atnet_assemble(c, prob_map_dev, all_p_dev, T, O, PH, PW, y0, x0, H, W, (cudaStream_t)stream);
 }
 
 }  // extern "C"

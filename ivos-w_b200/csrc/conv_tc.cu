@@ -55,6 +55,7 @@ struct TcParams {
     const __half* res_lo;
     __half* out_hi;
     __half* out_lo;
+    unsigned long long* sat_count;   // fp16 range guard events (ivosw_conv_saturation_count)
     TcTap taps[9];
 };
 
@@ -168,6 +169,10 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
     return pred != 0;
 }
+
+// bit 15 of a half lane is set iff that lane holds +-65504 (0x7BFF): the value the range guard clamps to.
+// (0x7BFF + 0x0401 = 0x8000, no carry between the lanes.)  OR-ed over a tile and tested once.
+__device__ __forceinline__ uint32_t sat_probe(uint32_t h2bits) { return (h2bits & 0x7FFF7FFFu) + 0x04010401u; }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -411,6 +416,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
                 for (int k = 0; k < 16; ++k) rf[g][k] = 0.f;
             int stage = 0, t_local = 0;                         // ring position of the residual blocks
+            uint32_t sat = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 if (has_res) {
@@ -496,6 +502,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             const __half2 h = __floats2half2_rn(a, b);
                             const float2 hf = __half22float2(h);
                             oh[q * 4 + u] = *reinterpret_cast<const uint32_t*>(&h);
+                            sat |= sat_probe(oh[q * 4 + u]);
                             ol[q * 4 + u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                         }
                     }
@@ -521,7 +528,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (leader) bulk_wait0();
+            if (sat & 0x80008000u) atomicAdd(P.sat_count, 1ull);
         } else {
+            uint32_t sat = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const long long m = (long long)mt * TC_BM + row;
@@ -572,6 +581,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             const __half2 h = __floats2half2_rn(a, b);
                             const float2 hf = __half22float2(h);
                             oh[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                            sat |= sat_probe(oh[j >> 1]);
                             ol[j >> 1] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                         }
                         uint4* ph = reinterpret_cast<uint4*>(P.out_hi + off);
@@ -589,6 +599,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (sat & 0x80008000u) atomicAdd(P.sat_count, 1ull);
         }
     }
     tc_fence_before();
@@ -676,11 +687,14 @@ template <int BN, int STAGES, bool STAGED>
 static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P, cudaStream_t s) {
     using S = TcSmem<BN, STAGES, STAGED>;
     static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
-    static bool attr = false;
-    if (!attr) {
+    // the opt-in above 48 KB of dynamic shared memory is a per-DEVICE function attribute: one Engine per device may
+    // live in the same process (engine.get_engine), so remember it per device, not per process
+    static bool attr[64] = {};
+    const int dv = c->device & 63;
+    if (!attr[dv]) {
         IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         S::TOTAL));
-        attr = true;
+        attr[dv] = true;
     }
     const int tiles = P.tiles_m * P.tiles_n;
     const int grid = tiles < c->sm_count ? tiles : c->sm_count;
@@ -740,6 +754,7 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     P.scale = L.scale; P.shift = L.shift;
     P.res_hi = residual ? residual->hi : nullptr; P.res_lo = residual ? residual->lo : nullptr;
     P.out_hi = out.hi; P.out_lo = out.lo;
+    P.sat_count = c->sat_count;
     for (int kh = 0; kh < L.k; ++kh)
         for (int kw = 0; kw < L.k; ++kw) {
             TcTap& t = P.taps[kh * L.k + kw];

@@ -11,6 +11,7 @@
 //   element-wise gradient clamp to +-1 (:157-159), Adam with L2 weight decay in the gradient (:101,160).
 // The stochastic hard target sync (:163-165) is the caller's decision (ivosw_dqn_sync_target).
 #include <cmath>
+#include <cstdio>
 
 #include "ivosw_internal.h"
 
@@ -213,6 +214,13 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict_
     if (i < n && !(act[i] > 0.f)) d[i] = 0.f;
 }
 
+// action[n] indexes the frame axis of the saved activations: a replay sample outside [0, T) would read (and, in the LSTM
+// chain, write) out of bounds.  The reference's gather() raises on such an index; so does this path, before touching anything.
+__global__ void check_actions_kernel(const int* __restrict__ action, int N, int T, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && (action[i] < 0 || action[i] >= T)) atomicExch(bad, i + 1);
+}
+
 __global__ void loss_reduce_kernel(const float* __restrict__ part, int N, float* __restrict__ loss) {
     __shared__ float red[32];
     float a = 0.f;
@@ -285,6 +293,23 @@ int dqn_update(ivosw_ctx* c, const float* state, const float* new_state, const i
     float* W = (float*)c->dqn_ws.p;
     float* grad = W + o_grad;
     const float* Pp = c->brain_params;
+    {   // validate the replay actions first (one tiny kernel + a 4-byte read; the step itself takes milliseconds)
+        if ((rc = ensure_pinned(c, 64))) return rc;
+        int* bad_dev = (int*)(W + o_loss) + 8;
+        IVOSW_CUDA(cudaMemsetAsync(bad_dev, 0, sizeof(int), s));
+        check_actions_kernel<<<(N + 255) / 256, 256, 0, s>>>(action, N, T, bad_dev);
+        IVOSW_CUDA(cudaGetLastError());
+        c->launches += 1;
+        IVOSW_CUDA(cudaMemcpyAsync(c->pinned_small, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+        IVOSW_CUDA(cudaStreamSynchronize(s));
+        const int bad = *(int*)c->pinned_small;
+        if (bad) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "invalid argument: action[%d] is outside [0, T=%d) (index out of range in gather)", bad - 1, T);
+            set_error(buf);
+            return IVOSW_ERR_INVALID;
+        }
+    }
     // ---- no-grad forwards on the new state (policy -> a*, target -> Q_next)
     if ((rc = launch_brain_ex(c, Pp, c->brain_whh_t, c->brain_d1t, new_state, N, T, W + o_qpn, (int*)(W + o_astar), nullptr, s)))
         return rc;

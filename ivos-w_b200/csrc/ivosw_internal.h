@@ -118,6 +118,9 @@ struct ivosw_ctx {
     float* fc_w = nullptr;           // 2048
     float fc_b = 0.f;
     std::vector<ivosw::ConvLayer> layers;
+    // fp16 range guard: epilogue threads whose tile produced a value clamped to +-65504 (split-fp16 planes cannot hold
+    // more) bump this device counter; ivosw_conv_saturation_count reads it.  0 on every in-range network.
+    unsigned long long* sat_count = nullptr;
 
     // workspace (grown on demand, per chunk of `chunk_cap` samples)
     int chunk_cap = 0;
@@ -222,6 +225,13 @@ int launch_manet_tail(ivosw_ctx* c, const float* logits, int T, int C, int h, in
                       float* all_p, cudaStream_t s);
 int launch_rough_roi(ivosw_ctx* c, const float* in, float* out, int B, int h, int w, int dist, int* empty_flag_dev,
                      cudaStream_t s);
+// ---- atnet_glue.cu
+int launch_reflect_pad(ivosw_ctx* c, const float* in, float* out, long long planes, int h, int w, int left, int right, int top,
+                       int bottom, cudaStream_t s);
+int launch_sigmoid_blend(ivosw_ctx* c, const float* logit, const float* prev, float* prob, float* blended, long long n,
+                         float alpha, float beta, cudaStream_t s);
+int launch_atnet_assemble(ivosw_ctx* c, const float* prob_map, float* all_p, int T, int O, int PH, int PW, int y0, int x0,
+                          int H, int W, cudaStream_t s);
 // ---- probe helper (NHWC -> NCHW)
 int launch_nhwc_to_nchw(ivosw_ctx* c, const float* in, float* out, int B, int HW, int C, cudaStream_t s);
 

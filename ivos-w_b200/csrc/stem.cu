@@ -102,10 +102,11 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float4* __restrict__
 
 int launch_stem(ivosw_ctx* c, int B, cudaStream_t s) {
     const size_t smem = (size_t)ST_K * 64 * 4 + (size_t)ST_PH * ST_PW * 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};          // per device (the attribute is not process-wide)
+    const int dv = c->device & 63;
+    if (!attr_set[dv]) {
         IVOSW_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dv] = true;
     }
     dim3 grid(128 / ST_TW, 128 / ST_TH, B);
     stem_conv_kernel<<<grid, 256, smem, s>>>((const float4*)c->crop.p, c->stem_w, c->stem_scale, c->stem_shift,

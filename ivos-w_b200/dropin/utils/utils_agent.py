@@ -14,26 +14,35 @@ The RL training bookkeeping of the reference file (goal_only_reward,
 agent_business, ...) is outside the scoring path and not reproduced here.
 """
 import random
+import weakref
 
 import numpy as np
 import torch
 
 from ivosw.engine import get_engine
 
-_CLIP_CACHE = {}   # device index -> (key, device tensor)
+_CLIP_CACHE = {}   # device index -> (weakref to the caller's CPU tensor, its _version, device copy)
 
 
 def _frames_on_device(all_F, device):
+    """The clip is uploaded once and reused for the 8 rounds of a (sequence, scribble) visit.  The cache entry is
+    tied to the IDENTITY of the caller's tensor object (weak reference) and its in-place version counter — not to its
+    address: a new clip that the allocator places at a recycled address must never be served the old frames."""
     dev = torch.device(device)
     if all_F.is_cuda:
         return all_F
-    key = (all_F.data_ptr(), tuple(all_F.shape), all_F._version)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     hit = _CLIP_CACHE.get(idx)
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    if hit is not None and hit[0]() is all_F and hit[1] == all_F._version:
+        return hit[2]
     t = all_F.to(dev, torch.float32, non_blocking=False)
-    _CLIP_CACHE[idx] = (key, t)
+
+    def _drop(ref, idx=idx):               # the source clip was collected: free its device copy too
+        cur = _CLIP_CACHE.get(idx)
+        if cur is not None and cur[0] is ref:
+            del _CLIP_CACHE[idx]
+
+    _CLIP_CACHE[idx] = (weakref.ref(all_F, _drop), all_F._version, t)
     return t
 
 

@@ -32,6 +32,9 @@ SYMBOLS = {
     "ivosw_dqn_load_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ivosw_dqn_sync_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ivosw_dqn_reset_optimizer": (C.c_int, [C.c_void_p]),
+    "ivosw_dqn_get_optimizer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p]),
+    "ivosw_dqn_set_optimizer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ivosw_conv_saturation_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.c_void_p]),
     "ivosw_dqn_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_float, C.c_float, C.c_float, _c_f, C.c_void_p, C.c_int, C.c_void_p]),
     "ivosw_dqn_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
@@ -57,6 +60,12 @@ SYMBOLS = {
     "ivosw_stage_times": (C.c_int, [C.c_void_p, _c_f, C.POINTER(C.c_longlong), C.c_int]),
     "ivosw_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_i,
                                    C.c_void_p]),
+    "ivosw_atnet_reflect_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_void_p]),
+    "ivosw_atnet_sigmoid_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                            C.c_float, C.c_float, C.c_void_p]),
+    "ivosw_atnet_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ivosw_rough_roi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ivosw_manet_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),

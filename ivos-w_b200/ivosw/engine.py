@@ -134,6 +134,28 @@ class Engine:
     def reset_optimizer(self):
         check(lib.ivosw_dqn_reset_optimizer(self._h))
 
+    def optimizer_state(self):
+        """Adam state of the policy network inside the library: dict(step, exp_avg, exp_avg_sq) — the two
+        moment vectors as flat CUDA tensors in blob order (Engine.unpack_brain gives them per parameter)."""
+        m = torch.empty((BRAIN_NUM_PARAMS,), device=self.device, dtype=torch.float32)
+        v = torch.empty_like(m)
+        step = C.c_longlong(0)
+        check(lib.ivosw_dqn_get_optimizer(self._h, _ptr(m), _ptr(v), C.byref(step), _stream(self.device)))
+        return {"step": int(step.value), "exp_avg": m, "exp_avg_sq": v}
+
+    def load_optimizer_state(self, state):
+        m = state["exp_avg"].to(self.device, torch.float32).contiguous().view(-1)
+        v = state["exp_avg_sq"].to(self.device, torch.float32).contiguous().view(-1)
+        assert m.numel() == BRAIN_NUM_PARAMS and v.numel() == BRAIN_NUM_PARAMS
+        check(lib.ivosw_dqn_set_optimizer(self._h, _ptr(m), _ptr(v), int(state["step"]), _stream(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def saturation_count(self, reset=True):
+        """(thread, tile) pairs of the split-fp16 encoder that clamped a value to +-65504 since the last reset."""
+        n = C.c_longlong(0)
+        check(lib.ivosw_conv_saturation_count(self._h, C.byref(n), 1 if reset else 0, _stream(self.device)))
+        return int(n.value)
+
     def dqn_update(self, state, new_state, action, reward_step, reward_done, gamma=0.95, lr=5e-6, weight_decay=5e-4,
                    want_grads=False, apply=True):
         """One Agent.update_agent step on CUDA tensors: state/new_state N x T x 2, action N, rewards N.
@@ -340,6 +362,39 @@ class Engine:
         B, _, h, w = x.shape
         out = torch.empty_like(x)
         check(lib.ivosw_rough_roi(self._h, _ptr(x), _ptr(out), B, h, w, dist, _stream(self.device)))
+        return out
+
+    # ------------------------------------------------------------------ ATNet glue (utils/utils_atnet.py)
+    def reflect_pad(self, x, left, right, top, bottom):
+        """torch.nn.ReflectionPad2d((left, right, top, bottom)) on an N x C x h x w CUDA fp32 tensor."""
+        x = self._dev32(x)
+        N, Cn, h, w = x.shape
+        out = torch.empty((N, Cn, h + top + bottom, w + left + right), device=self.device, dtype=torch.float32)
+        check(lib.ivosw_atnet_reflect_pad(self._h, _ptr(x), _ptr(out), N * Cn, h, w, left, right, top, bottom,
+                                          _stream(self.device)))
+        return out
+
+    def sigmoid_blend(self, logit, prev_inplace=None, alpha=1.0):
+        """prob = sigmoid(logit) (returned, logit's shape).  With ``prev_inplace`` (a contiguous CUDA tensor with
+        logit.numel() elements, e.g. prob_map_of_frames[frame]): prev_inplace <- alpha*prob + (1-alpha)*prev_inplace."""
+        logit = self._dev32(logit)
+        prob = torch.empty_like(logit)
+        if prev_inplace is None:
+            check(lib.ivosw_atnet_sigmoid_blend(self._h, _ptr(logit), None, _ptr(prob), _ptr(prob), logit.numel(), 1.0, 0.0,
+                                                _stream(self.device)))
+            return prob
+        assert prev_inplace.is_cuda and prev_inplace.dtype == torch.float32 and prev_inplace.is_contiguous()
+        assert prev_inplace.numel() == logit.numel()
+        check(lib.ivosw_atnet_sigmoid_blend(self._h, _ptr(logit), _ptr(prev_inplace), _ptr(prob), _ptr(prev_inplace),
+                                            logit.numel(), float(alpha), float(1 - alpha), _stream(self.device)))
+        return prob
+
+    def atnet_assemble(self, prob_map, y0, x0, H, W):
+        """prob_map: T x O x PH x PW CUDA fp32 -> all_P T x (O+1) x H x W (channel 0 zero, crop at (y0, x0))."""
+        prob_map = self._dev32(prob_map)
+        T, O, PH, PW = prob_map.shape
+        out = torch.empty((T, O + 1, H, W), device=self.device, dtype=torch.float32)
+        check(lib.ivosw_atnet_assemble(self._h, _ptr(prob_map), _ptr(out), T, O, PH, PW, y0, x0, H, W, _stream(self.device)))
         return out
 
     # ------------------------------------------------------------------ helpers

@@ -1,7 +1,7 @@
-"""Minimal stand-in for the reference's models/momory_pool.py::ReplayMemory (ring buffer only).
-The pandas/CSV mirror (load_from_csv / push_to_csv, momory_pool.py:44-153) is training-time
-bookkeeping outside the scoring path (OUT OF SCOPE) and is not reproduced."""
+"""TEST DOUBLE for the checkout's models/momory_pool.py (ring buffer only; the real one adds a pandas/CSV mirror)."""
 import random
+
+IS_TEST_DOUBLE = True
 
 
 class ReplayMemory(object):

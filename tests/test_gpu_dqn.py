@@ -123,13 +123,8 @@ def test_dropin_agent_update_matches_reference(golden_dir):
     """The drop-in Agent.update_agent (same signature / sample dict as agent.py:103) against the reference fixture."""
     import sys
     from types import SimpleNamespace
-    REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = os.path.join(REPO, "ivos-w_b200", "dropin")
-    for m in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")]:
-        del sys.modules[m]
-    sys.path.insert(0, p)
-    import models.agent as A
-    sys.path.remove(p)
+    from tests import doubles
+    A = doubles.load_dropin().A
     g = np.load(os.path.join(golden_dir, "dqn_step.npz"))
     cfg = SimpleNamespace(phase="train", agent=SimpleNamespace(memory_size=10, gamma=0.95, eps_start=0.7, eps_end=0.25,
                           eps_decay=500, update_rate=0.05, lr=5e-6, weight_decay=5e-4), data=SimpleNamespace(subset="train"))

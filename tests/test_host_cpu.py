@@ -79,15 +79,12 @@ def test_no_cpu_fallback(built_lib):
 
 
 def _dropin():
-    p = os.path.join(REPO, "ivos-w_b200", "dropin")
-    for m in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")]:
-        del sys.modules[m]
-    sys.path.insert(0, p)
-    import models.agent as A
-    import models.assessment as S
-    import utils.utils_agent as U
-    sys.path.remove(p)
-    return A, S, U
+    """drop-in modules imported the way an entry script gets them: ivosw.hook over a (test double) checkout"""
+    from tests import doubles
+    d = doubles.load_dropin()
+    assert d.A.__file__.startswith(os.path.join(REPO, "ivos-w_b200", "dropin"))
+    assert d.misc.__file__.startswith(doubles.CHECKOUT)          # the checkout's own utils.misc is still reachable
+    return d.A, d.S, d.U
 
 
 def test_dropin_state_dict_contract(built_lib):

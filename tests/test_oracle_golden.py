@@ -179,3 +179,58 @@ def test_assess_train_step(golden_dir, sampler, monkeypatch):
                                    rtol=1e-4, atol=1e-5, err_msg=k)
     no_grad = sorted(k for k, v in st.params.items() if v.grad is None)
     assert no_grad == [str(k) for k in g["no_grad_params"]]
+
+
+def test_atnet_wrapper_oracle_vs_reference_golden(golden_dir):
+    """oracle/atnet_glue_ref.py (restatement of utils/utils_atnet.py:72-159) replays the three interaction rounds the
+    reference's own run_VOS_singleiact produced tests/golden/atnet_round.npz from — same stand-in network and loader
+    (tests/doubles) — and must reproduce prob_map_of_frames and all_P bit for bit on CPU."""
+    import importlib.util
+    import sys
+    from oracle import atnet_glue_ref as og
+    here = os.path.dirname(os.path.abspath(__file__))
+    dbl = os.path.join(here, "doubles")
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    mk = load("mk_atnet", os.path.join(golden_dir, "make_golden_atnet.py"))
+    lutils = load("dbl_lutils", os.path.join(dbl, "atnet_repo", "libs", "utils.py"))
+    dd = load("dbl_davis", os.path.join(dbl, "checkout", "datasets", "davis_dataset.py"))
+    atnet = load("dbl_atnet", os.path.join(dbl, "atnet_repo", "networks", "atnet.py"))
+    g = np.load(os.path.join(golden_dir, "atnet_round.npz"))
+    T, n_obj, H, W, h1, h2, w1, w2 = [int(v) for v in g["meta"]]
+    cfg = mk.config()
+    pad_info = ((h1, h2), (w1, w2))
+
+    def frames_fn(idx):
+        img = (dd.synthetic_frame(idx) - cfg.mean) / cfg.var                       # libs.custom_transforms doubles
+        return torch.from_numpy(img.transpose(2, 0, 1).copy()).float()[None].expand(n_obj, -1, -1, -1)
+
+    prob_map = torch.zeros((T, n_obj, H + h1 + h2, W + w1 + w2))
+    final_masks = np.zeros((T, H, W))
+    r5_3, r5_6 = [], []
+    net = atnet.ATnet()
+    for rnd, annotated in enumerate(mk.ROUNDS, start=1):
+        now = annotated[-1]
+        sl = mk.scribbles_for(now, rnd)['scribbles']
+        planes = []
+        for obj in range(1, n_obj + 1):                                            # utils_atnet.py:31-52
+            if rnd == 1:
+                pos = lutils.scribble_to_image(sl, now, obj, dilation=cfg.scribble_dilation_param, prev_mask=final_masks[now])
+                planes.append(np.stack([np.ones_like(pos) / 2, pos, np.zeros_like(pos)], 0))
+            else:
+                pos, neg = lutils.scribble_to_image(sl, now, obj, dilation=cfg.scribble_dilation_param,
+                                                    prev_mask=final_masks[now], blur=True, singleimg=False,
+                                                    seperate_pos_neg=True)
+                planes.append(np.stack([(final_masks[now] == obj).astype(np.float32), pos, neg], 0))
+        prop_list = lutils.get_prop_list(list(annotated), now, T)
+        og.run_round(net, frames_fn, np.stack(planes, 0), prop_list, list(annotated), prob_map, pad_info, r5_3, r5_6)
+        np.testing.assert_array_equal(prob_map.numpy(), g["r%d_prob_map" % rnd])
+        np.testing.assert_array_equal(og.assemble_all_p(prob_map, h1, h2, w1, w2).numpy(), g["r%d_all_P" % rnd])
+        final_masks = g["r%d_masks" % rnd].astype(np.float64)
+    # pieces: reflection pad against torch's module
+    x = torch.randn(2, 3, 9, 11)
+    np.testing.assert_array_equal(og.reflect_pad(x, ((3, 2), (4, 1))).numpy(), torch.nn.ReflectionPad2d((4, 1, 3, 2))(x).numpy())
