@@ -26,33 +26,43 @@ def activate(checkout=CHECKOUT):
 def deactivate(checkout=CHECKOUT):
     from ivosw import hook
     hook.uninstall()
+    _only_repo(None)
     purge()
     if checkout in sys.path:
         sys.path.remove(checkout)
 
 
+def _only_repo(which):
+    """exactly one of the external-repo doubles on sys.path (each has its own top-level `config` / `networks`, as the
+    real MANet / ATNet checkouts do: an entry script only ever appends one of them)"""
+    for extra in ("manet_repo", "atnet_repo", "ipn_repo"):
+        p = os.path.join(HERE, extra)
+        while p in sys.path:
+            sys.path.remove(p)
+    purge(("config", "networks", "dataloaders", "libs"))
+    if which:
+        sys.path.insert(1, os.path.join(HERE, which))
+
+
 def load_dropin(with_manet=False, with_atnet=False):
     """The drop-in modules as an entry script sees them: imported under the reference's names, through the hook, over
     the double checkout.  Returns a namespace (A = models.agent, S = models.assessment, U = utils.utils_agent,
-    M = utils.utils_manet, AT = utils.utils_atnet)."""
+    M = utils.utils_manet, AT = utils.utils_atnet).  With with_atnet the ATNet repo double stays on sys.path afterwards
+    (tests import its stand-in network from there)."""
     from types import SimpleNamespace
     activate()
-    for extra, on in (("manet_repo", with_manet), ("atnet_repo", with_atnet)):
-        p = os.path.join(HERE, extra)
-        if p in sys.path:
-            sys.path.remove(p)
-        if on:
-            sys.path.insert(1, p)
+    _only_repo(None)
     import models.agent as A
     import models.assessment as S
     import utils.misc as misc
     import utils.utils_agent as U
     ns = SimpleNamespace(A=A, S=S, U=U, misc=misc, M=None, AT=None)
     if with_manet:
+        _only_repo("manet_repo")
         import utils.utils_manet as M
         ns.M = M
     if with_atnet:
-        purge(("config",))
+        _only_repo("atnet_repo")
         import utils.utils_atnet as AT
         ns.AT = AT
     return ns
