@@ -28,6 +28,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 // bumped whenever a workspace buffer moves: captured CUDA graphs hold raw pointers and must be rebuilt
 static unsigned long long g_alloc_epoch = 1;
+unsigned long long current_alloc_epoch() { return g_alloc_epoch; }
 
 int ensure(DeviceBuffer& b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return IVOSW_OK;
@@ -259,34 +260,49 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
                 }
             }
         } else {
+            if (c->stack_on) {
+                // one persistent launch for all 52 layers (conv_stack.cu)
+                SplitAct stage_out[4];
+                if ((rc = launch_conv_stack(c, xs, B, terms, s, &xs, c->probes_on ? stage_out : nullptr))) return rc;
+                if (c->probes_on) {
+                    static const int C_[4] = {256, 512, 1024, 2048}, HW_[4] = {64, 32, 16, 8};
+                    for (int k = 0; k < 4; ++k) {
+                        const size_t n = (size_t)B * HW_[k] * HW_[k] * C_[k];
+                        if ((rc = ensure(c->probe_buf[2 + k], n * sizeof(float)))) return rc;
+                        if ((rc = launch_merge(c, stage_out[k], (float*)c->probe_buf[2 + k].p, (long long)n, terms == 3, s)))
+                            return rc;
+                    }
+                }
+            } else {
             // tensor-core path: activations live as split-fp16 planes inside the same workspace buffers
-            const SplitAct t1 = split_view(c->actT1), t2 = split_view(c->actT2), ds = split_view(c->actDS);
-            const SplitAct outs[2] = {split_view(c->actX), split_view(c->actY)};
-            int flip = 0, stage_probe = 2;
-            for (size_t li = 0; li < c->layers.size(); ++li) {
-                const ConvLayer& L = c->layers[li];
-                if (L.first_of_block) {
-                    if ((rc = launch_conv_tc(c, L, xs, nullptr, t1, B, terms, s))) return rc;
-                } else if (L.k == 3) {
-                    if ((rc = launch_conv_tc(c, L, t1, nullptr, t2, B, terms, s))) return rc;
-                } else if (L.is_downsample) {
-                    if ((rc = launch_conv_tc(c, L, xs, nullptr, ds, B, terms, s))) return rc;
-                } else {
-                    const SplitAct* res = L.residual == 2 ? &ds : &xs;
-                    const SplitAct y = outs[flip];
-                    if ((rc = launch_conv_tc(c, L, t2, res, y, B, terms, s))) return rc;
-                    xs = y;
-                    flip ^= 1;
-                    const bool stage_end_ = (li + 1 == c->layers.size()) ||
-                                            (li + 3 < c->layers.size() && c->layers[li + 3].is_downsample);
-                    if (stage_end_) {
-                        if (c->probes_on) {
-                            const size_t n = (size_t)B * L.out_hw * L.out_hw * L.cout;
-                            if ((rc = ensure(c->probe_buf[stage_probe], n * sizeof(float)))) return rc;
-                            if ((rc = launch_merge(c, xs, (float*)c->probe_buf[stage_probe].p, (long long)n, terms == 3, s)))
-                                return rc;
+                const SplitAct t1 = split_view(c->actT1), t2 = split_view(c->actT2), ds = split_view(c->actDS);
+                const SplitAct outs[2] = {split_view(c->actX), split_view(c->actY)};
+                int flip = 0, stage_probe = 2;
+                for (size_t li = 0; li < c->layers.size(); ++li) {
+                    const ConvLayer& L = c->layers[li];
+                    if (L.first_of_block) {
+                        if ((rc = launch_conv_tc(c, L, xs, nullptr, t1, B, terms, s))) return rc;
+                    } else if (L.k == 3) {
+                        if ((rc = launch_conv_tc(c, L, t1, nullptr, t2, B, terms, s))) return rc;
+                    } else if (L.is_downsample) {
+                        if ((rc = launch_conv_tc(c, L, xs, nullptr, ds, B, terms, s))) return rc;
+                    } else {
+                        const SplitAct* res = L.residual == 2 ? &ds : &xs;
+                        const SplitAct y = outs[flip];
+                        if ((rc = launch_conv_tc(c, L, t2, res, y, B, terms, s))) return rc;
+                        xs = y;
+                        flip ^= 1;
+                        const bool stage_end_ = (li + 1 == c->layers.size()) ||
+                                                (li + 3 < c->layers.size() && c->layers[li + 3].is_downsample);
+                        if (stage_end_) {
+                            if (c->probes_on) {
+                                const size_t n = (size_t)B * L.out_hw * L.out_hw * L.cout;
+                                if ((rc = ensure(c->probe_buf[stage_probe], n * sizeof(float)))) return rc;
+                                if ((rc = launch_merge(c, xs, (float*)c->probe_buf[stage_probe].p, (long long)n, terms == 3, s)))
+                                    return rc;
+                            }
+                            ++stage_probe;
                         }
-                        ++stage_probe;
                     }
                 }
             }
@@ -419,6 +435,7 @@ int ivosw_create(int device, int conv_mode, ivosw_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->chunk_cap = chunk_cap_default();
     { const char* g = getenv("IVOSW_GRAPHS"); c->graphs_on = !(g && atoi(g) == 0); }
+    { const char* g = getenv("IVOSW_STACK"); c->stack_on = !(g && atoi(g) == 0); }      // 0: one launch per layer (conv_tc.cu)
     c->layers = make_resnet50_layers();
     if (cudaMalloc(&c->sat_count, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(c->sat_count, 0, sizeof(unsigned long long)) != cudaSuccess) {
@@ -443,6 +460,8 @@ void ivosw_destroy(ivosw_ctx* c) {
     if (c->adam_v) cudaFree(c->adam_v);
     release(c->dqn_ws);
     if (c->sat_count) cudaFree(c->sat_count);
+    conv_stack_release(c);
+    release(c->stack_arena);
     if (c->stem_w) cudaFree(c->stem_w);
     if (c->stem_scale) cudaFree(c->stem_scale);
     if (c->stem_shift) cudaFree(c->stem_shift);

@@ -26,21 +26,9 @@
 // variant (per-thread 16-byte stores; the few-tile res5 layers).  Persistent CTAs walk the (m-tile,
 // n-tile) list n-fastest; TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Measurements behind these choices: DESIGN.md 4.3, profiles/r1_tc_ceiling.md.
-#include <cuda.h>
-
-#include "ivosw_internal.h"
+#include "tc_common.cuh"
 
 namespace ivosw {
-
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;           // fp16 elements per K block = 128 bytes = one swizzle row
-// direct-epilogue variants: 2 + 8 warps; staged variant: 2 + 16 warps (its epilogue is issue-bound:
-// ~15 instructions per output element, so it gets four warps per TMEM lane quarter)
-__host__ __device__ constexpr int tc_threads(bool staged) { return staged ? 576 : 320; }
-__host__ __device__ constexpr int tc_epi_warps(bool staged) { return staged ? 16 : 8; }
-constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: no legitimate wait is this long
-
-struct TcTap { int c_add, w_add, p, h_add; };
 
 struct TcParams {
     int M, Cout, Cin;
@@ -58,150 +46,6 @@ struct TcParams {
     unsigned long long* sat_count;   // fp16 range guard events (ivosw_conv_saturation_count)
     TcTap taps[9];
 };
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    long long t0 = 0;
-    for (uint32_t it = 0;; ++it) {
-        uint32_t done;
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
-        if ((it & 1023u) == 1023u) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > WAIT_TIMEOUT_CYCLES) __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem], M = 128, kind::f16, issued by ONE thread
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives on `bar` when all previously issued MMAs of this thread have completed (implies fence::before)
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row atoms of 1024 bytes)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address        bits [0,14)
-    d |= (uint64_t)1 << 16;                               // leading byte offset  (ignored for SW128 K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset   bits [32,46): 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                               // descriptor version   (sm_100)
-    d |= (uint64_t)2 << 61;                               // layout type          SWIZZLE_128B
-    return d;
-}
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
-
-// bit 15 of a half lane is set iff that lane holds +-65504 (0x7BFF): the value the range guard clamps to.
-// (0x7BFF + 0x0401 = 0x8000, no carry between the lanes.)  OR-ed over a tile and tested once.
-__device__ __forceinline__ uint32_t sat_probe(uint32_t h2bits) { return (h2bits & 0x7FFF7FFFu) + 0x04010401u; }
-
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// ------------------------------------------------------------------------------------------------
-// kernel
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void group_bar(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 
 // STAGED epilogue (the 1x1 "expand" layers, whose output + residual traffic dominates).  Next to the
 // operand ring sits one 32 KB staging buffer (hi + lo planes of a 128 x 64 half tile, 128B-swizzled).  Per
@@ -647,7 +491,7 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
 }
 
 // 5-d view of an NHWC fp16 activation plane whose boxes are "whole rows of the OUTPUT grid".
-static int encode_act_map(CUtensorMap* map, const __half* base, int B, int H, int C, int stride, int out_hw) {
+int encode_act_map(CUtensorMap* map, const __half* base, int B, int H, int C, int stride, int out_hw) {
     const int W = H;
     const int Wb = out_hw;
     const int Hb = (TC_BM / Wb) < out_hw ? (TC_BM / Wb) : out_hw;
@@ -669,14 +513,14 @@ static int encode_act_map(CUtensorMap* map, const __half* base, int B, int H, in
     return encode_map(map, base, 5, dims, strides, box);
 }
 
-static int encode_w_map(CUtensorMap* map, const __half* base, int K, int Cout, int BN) {
+int encode_w_map(CUtensorMap* map, const __half* base, int K, int Cout, int BN) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(__half)};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
     return encode_map(map, base, 2, dims, strides, box);
 }
 
-static int encode_out_map(CUtensorMap* map, const __half* base, long long M, int Cout) {
+int encode_out_map(CUtensorMap* map, const __half* base, long long M, int Cout) {
     cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)M};
     cuuint64_t strides[1] = {(cuuint64_t)Cout * sizeof(__half)};
     cuuint32_t box[2] = {64, (cuuint32_t)TC_BM};

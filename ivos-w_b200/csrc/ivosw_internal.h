@@ -160,6 +160,13 @@ struct ivosw_ctx {
     cudaStream_t graph_stream = nullptr;
     cudaEvent_t g_ev1 = nullptr, g_ev2 = nullptr;
 
+    // persistent conv-stack kernel (conv_stack.cu): one output buffer per layer, cached plans
+    ivosw::DeviceBuffer stack_arena;
+    int stack_arena_cap = 0;
+    int chunk_cap_seen = 0;
+    void* stack_state = nullptr;
+    bool stack_on = true;
+
     // host-staged rounds
     ivosw::DeviceBuffer stage_frames, stage_probs, scores_all;
     std::vector<cudaEvent_t> chunk_evts;
@@ -201,6 +208,10 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
                    int B, int terms, cudaStream_t s);
 int launch_split(ivosw_ctx* c, const float* in, const SplitAct& out, long long n, cudaStream_t s);
 int launch_merge(ivosw_ctx* c, const SplitAct& in, float* out, long long n, int use_lo, cudaStream_t s);
+// ---- conv_stack.cu
+int launch_conv_stack(ivosw_ctx* c, const SplitAct& in, int B, int terms, cudaStream_t s, SplitAct* out, SplitAct* stage_out);
+void conv_stack_release(ivosw_ctx* c);
+unsigned long long current_alloc_epoch();
 // ---- head.cu
 int launch_gap_fc(ivosw_ctx* c, const float* r5, int B, float* scores, cudaStream_t s);
 int launch_gap_fc_split(ivosw_ctx* c, const SplitAct& r5, int use_lo, int B, float* scores, cudaStream_t s);
