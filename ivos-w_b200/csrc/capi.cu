@@ -388,8 +388,7 @@ static int run_graphed(ivosw_ctx* c, ivosw_ctx::GraphKey key, cudaStream_t s, F&
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
             drop_graph(c, *e);
-            if (rc != IVOSW_OK) return rc;
-            return fn(s);           // could not capture (e.g. a buffer had to grow): run eagerly
+            return fn(s);           // could not capture (a buffer had to grow, a plan had to be rebuilt): run eagerly
         }
         const cudaError_t ie = cudaGraphInstantiate(&e->exec, g, 0);
         cudaGraphDestroy(g);
@@ -435,7 +434,7 @@ int ivosw_create(int device, int conv_mode, ivosw_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->chunk_cap = chunk_cap_default();
     { const char* g = getenv("IVOSW_GRAPHS"); c->graphs_on = !(g && atoi(g) == 0); }
-    { const char* g = getenv("IVOSW_STACK"); c->stack_on = !(g && atoi(g) == 0); }      // 0: one launch per layer (conv_tc.cu)
+    { const char* g = getenv("IVOSW_STACK"); c->stack_on = g && atoi(g) != 0; }   // 1: conv_stack.cu (one persistent launch) instead of one launch per layer
     c->layers = make_resnet50_layers();
     if (cudaMalloc(&c->sat_count, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(c->sat_count, 0, sizeof(unsigned long long)) != cudaSuccess) {
@@ -660,6 +659,7 @@ int ivosw_assess_load(ivosw_ctx* c, const float* blob, size_t n_floats) {
     if ((rc = upload(&c->fc_w, p, 2048))) return rc;
     c->fc_b = p[2048];
     c->assess_loaded = true;
+    ++c->assess_version;
     ++g_alloc_epoch;   // scalars (fc bias, mean, std) are baked into captured kernel arguments
     return IVOSW_OK;
 }

@@ -16,8 +16,8 @@
 // The tile code itself is the staged-epilogue variant of conv_tc.cu (TMA -> 3-slot smem ring -> tcgen05.mma into two
 // TMEM accumulator stages -> 16 epilogue warps -> swizzled staging buffer -> TMA store), with the tile width (64 / 128
 // output channels), the tap list, the tensor maps and the BatchNorm vectors read per tile from a layer table in
-// global memory, plus a 19th warp whose first lane owns the output stores: it sends the staged half tiles, waits for the
-// writes to COMPLETE (cp.async.bulk.wait_group 0, not .read) and only then publishes the tile.
+// global memory, plus two store warps (one lane each, alternating tiles) that own the output stores: they send the staged
+// half tiles, wait for the writes to COMPLETE (cp.async.bulk.wait_group 0, not .read) and only then publish the tile.
 //
 // Cross-CTA protocol (who may read what, when):
 //   producer of a tile    TMA stores (async proxy) -> cp.async.bulk.wait_group 0 -> fence.proxy.async ->
@@ -30,6 +30,7 @@
 // Every buffer is written exactly once per launch (one output buffer per layer), so there are no WAR hazards to order.
 // All waits are bounded and trap.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -45,7 +46,8 @@ constexpr int CS_STG_BYTES = 2 * CS_A_BYTES;
 constexpr int CS_BAR_OFF = CS_STG_OFF + CS_STG_BYTES;
 constexpr int CS_SMEM = CS_BAR_OFF + 256 + 1024 /*align slack*/;
 constexpr int CS_EPI_WARPS = 16;
-constexpr int CS_THREADS = 32 * (2 + CS_EPI_WARPS + 1);             // producer, MMA, 16 epilogue, store
+constexpr int CS_STORE_WARPS = 2;                                   // alternate tiles: one lane's completion wait overlaps the other's stores
+constexpr int CS_THREADS = 32 * (2 + CS_EPI_WARPS + CS_STORE_WARPS);   // producer, MMA, 16 epilogue, store
 static_assert(CS_SMEM <= 232448, "shared memory budget (227 KB)");
 
 struct alignas(64) CsLayer {
@@ -71,6 +73,8 @@ struct CsParams {
     int done_stride;
     int terms;
     unsigned long long* sat_count;
+    unsigned long long* prof;                  // measurement (IVOSW_STACK_PROFILE): [layer] cycles between tile completions
+                                               // per CTA, [64 + layer] cycles the producer spent waiting for dependencies
 };
 
 struct CsTile { int layer, mt, nt; };
@@ -100,6 +104,7 @@ __device__ __forceinline__ void cs_wait_done(const int* ctr, int need) {
     }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_constant__ CsParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -109,9 +114,9 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
     uint64_t* tfull_bar = bars + 6;                     // [2] accumulator stage complete
     uint64_t* tempty_bar = bars + 8;                    // [2] accumulator stage drained (16 warps)
     uint64_t* res_full = bars + 10;                     // [2] residual block of the r-th residual tile (r & 1)
-    uint64_t* stg_full = bars + 12;                     // staging buffer written (16 warps)
-    uint64_t* stg_empty = bars + 13;                    // staging buffer read by the TMA store (store thread)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* stg_full = bars + 12;                     // [2] staging buffer written (16 warps); index = tile parity in this CTA
+    uint64_t* stg_empty = bars + 14;                    // [2] staging buffer read out by the TMA store (store lane of that parity)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool x3 = P.terms == 3;
@@ -123,8 +128,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
             mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CS_EPI_WARPS);
             mbar_init(&res_full[i], 1);
         }
-        mbar_init(stg_full, CS_EPI_WARPS);
-        mbar_init(stg_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&stg_full[i], CS_EPI_WARPS); mbar_init(&stg_empty[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -139,10 +143,51 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int cur = 0, r_local = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        // Lane 0 issues the TMA loads of tile i.  Lanes 1..31 meanwhile poll the dependency counters of tile i + 1, one
+        // counter per lane, so that the acquire round trips to L2 (~700 cycles each, up to five per tile: a 3x3 tile reads
+        // three producer m-tiles, a stride-2 tile four, plus the residual's) are paid once, in parallel, and a tile ahead
+        // of their use instead of serially in front of every tile's first load.
+        int stage = 0; uint32_t phase = 0;
+        int cur = 0, r_local = 0;
+        int cur_next = 0;
+        // what lanes >= 1 do: wait until everything tile `t` reads has been stored (see the protocol above)
+        auto wait_deps = [&](int t) {
+            int tiles_n;
+            const CsTile T = cs_decode(P, t, cur_next, tiles_n);
+            const CsLayer* L = P.layers + T.layer;
+            const int in_layer = __ldg(&L->in_layer), res_layer = __ldg(&L->res_layer);
+            const long long w0 = (PROF && lane == 1) ? clock64() : 0;
+            int n_in = 0, mlo = 0;
+            if (in_layer >= 0) {
+                const int out_hw = __ldg(&L->out_hw), in_hw = __ldg(&L->in_hw), k = __ldg(&L->k), stride = __ldg(&L->stride),
+                          pad = __ldg(&L->pad);
+                const int pix_per_img = out_hw * out_hw;
+                const int m0 = T.mt * TC_BM;
+                const int n_img = m0 / pix_per_img;
+                const int h0 = (m0 - n_img * pix_per_img) / out_hw;
+                const int Hb = min(TC_BM / out_hw, out_hw);                 // output rows per image in this tile
+                const int Nb = max(1, TC_BM / pix_per_img);                 // images per tile (8x8: 2)
+                const int r_lo = max(0, stride * h0 - pad);
+                const int r_hi = min(in_hw - 1, stride * (h0 + Hb - 1) - pad + (k - 1));
+                const long long in_img = (long long)in_hw * in_hw;
+                mlo = (int)((n_img * in_img + (long long)r_lo * in_hw) / TC_BM);
+                int mhi = (int)(((n_img + Nb - 1) * in_img + (long long)r_hi * in_hw + in_hw - 1) / TC_BM);
+                mhi = min(mhi, __ldg(&L->in_m_tiles) - 1);
+                n_in = mhi - mlo + 1;
+                const int need = __ldg(&L->in_need);
+                const int* ctr = P.done + (long long)in_layer * P.done_stride;
+                for (int j = lane - 1; j < n_in; j += 30) cs_wait_done(ctr + mlo + j, need);      // lanes 1..30
+            }
+            if (lane == 31 && __ldg(&L->has_res) && res_layer >= 0)
+                cs_wait_done(P.done + (long long)res_layer * P.done_stride + T.mt, __ldg(&L->res_need));
+            if (PROF && lane == 1) atomicAdd(P.prof + 64 + T.layer, (unsigned long long)(clock64() - w0));
+        };
+        if (lane >= 1 && (int)blockIdx.x < P.total_tiles) wait_deps(blockIdx.x);
+        __syncwarp();
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+            if (lane >= 1) {
+                if (tile + (int)gridDim.x < P.total_tiles) wait_deps(tile + gridDim.x);
+            } else {
                 int tiles_n;
                 const CsTile T = cs_decode(P, tile, cur, tiles_n);
                 const CsLayer* L = P.layers + T.layer;
@@ -152,24 +197,6 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
                 const int m0 = T.mt * TC_BM;
                 const int n_img = m0 / pix_per_img;
                 const int h0 = (m0 - n_img * pix_per_img) / out_hw;
-                // ---- wait until everything this tile reads has been stored (see the protocol above)
-                const int in_layer = __ldg(&L->in_layer), res_layer = __ldg(&L->res_layer);
-                if (in_layer >= 0) {
-                    const int in_hw = __ldg(&L->in_hw), k = __ldg(&L->k), stride = __ldg(&L->stride), pad = __ldg(&L->pad);
-                    const int Hb = min(TC_BM / out_hw, out_hw);                 // output rows per image in this tile
-                    const int Nb = max(1, TC_BM / pix_per_img);                 // images per tile (8x8: 2)
-                    const int r_lo = max(0, stride * h0 - pad);
-                    const int r_hi = min(in_hw - 1, stride * (h0 + Hb - 1) - pad + (k - 1));
-                    const long long in_img = (long long)in_hw * in_hw;
-                    const int mlo = (int)((n_img * in_img + (long long)r_lo * in_hw) / TC_BM);
-                    int mhi = (int)(((n_img + Nb - 1) * in_img + (long long)r_hi * in_hw + in_hw - 1) / TC_BM);
-                    mhi = min(mhi, __ldg(&L->in_m_tiles) - 1);
-                    const int need = __ldg(&L->in_need);
-                    const int* ctr = P.done + (long long)in_layer * P.done_stride;
-                    for (int m = mlo; m <= mhi; ++m) cs_wait_done(ctr + m, need);
-                }
-                if (has_res && res_layer >= 0)
-                    cs_wait_done(P.done + (long long)res_layer * P.done_stride + T.mt, __ldg(&L->res_need));
                 asm volatile("fence.proxy.async;" ::: "memory");     // acquire (generic proxy) before the TMA reads (async proxy)
                 // ---- operand blocks
                 const uint32_t tx_bytes = x3 ? (uint32_t)(2 * CS_A_BYTES + 2 * bn * 128) : (uint32_t)(CS_A_BYTES + bn * 128);
@@ -202,6 +229,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
                     ++r_local;
                 }
             }
+            __syncwarp();          // tile + gridDim.x may be loaded: its inputs are complete (and ordered before lane 0's loads)
         }
     } else if (warp == 1) {
         // ====================================== MMA issuer ======================================
@@ -216,12 +244,17 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
             const int bn = li.x, num_kb = li.z;
             const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const bool prof = PROF && lane == 0;
+            long long c0 = prof ? clock64() : 0, w_full = 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            if (prof) { const long long c1 = clock64(); atomicAdd(P.prof + 448 + T.layer, (unsigned long long)(c1 - c0)); }
             tc_fence_after();
             const uint32_t d0 = tmem_base + (uint32_t)(acc * 256);
             const uint32_t d1 = d0 + (uint32_t)bn;
             for (int kb = 0; kb < num_kb; ++kb) {
+                if (prof) c0 = clock64();
                 mbar_wait(&full_bar[stage], (full_bits >> stage) & 1u);
+                if (prof) w_full += clock64() - c0;
                 full_bits ^= 1u << stage;
                 tc_fence_after();
                 const uint32_t st = smem_base + (uint32_t)(stage * CS_STAGE_BYTES);
@@ -245,6 +278,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
                 __syncwarp();
                 if (++stage == CS_STAGES) stage = 0;
             }
+            if (prof) atomicAdd(P.prof + 384 + T.layer, (unsigned long long)w_full);
             if (li.w) { if (++stage == CS_STAGES) stage = 0; }        // the residual block's ring position
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -257,10 +291,12 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
         uint32_t soff[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) soff[q] = (uint32_t)row * 128u + (uint32_t)(((2 * csub + q) ^ (row & 7)) << 4);
-        float rf[2][16];
         int acc = 0; uint32_t acc_phase = 0;
         int stage = 0, r_local = 0, cur = 0;
-        uint32_t se_phase = 0;                  // phase of stg_empty this thread waits for next
+        // the staging buffer is handed to the store lane of the tile's parity (see "store lanes" below); before it is
+        // rewritten, the previous pass must have been read out
+        uint32_t passes[2] = {0, 0};            // passes handed to each store lane so far
+        int prev_owner = -1, t_cta = 0;
         uint32_t sat = 0;
         const uint32_t stg_hi = smem_u32(smem + CS_STG_OFF), stg_lo = stg_hi + TC_BM * 128;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -270,17 +306,61 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
             const int4 li = __ldg(reinterpret_cast<const int4*>(&L->bn));
             const int bn = li.x, num_kb = li.z;
             const bool has_res = li.w != 0;
-            const bool relu = __ldg(&L->relu) != 0;
+            // ReLU and the fp16 range guard as ONE clamp: [0, 65504] or [-65504, 65504]
+            const float lo_clamp = __ldg(&L->relu) != 0 ? 0.f : -65504.f;
             const float* scale = L->scale;
             const float* shift = L->shift;
             const int np = bn >> 6;                                          // passes of 64 columns
+            const bool prof = PROF && threadIdx.x == 64;
+            const long long e0 = prof ? clock64() : 0;
+            long long e_res = 0, e_tf = 0, e_stg = 0, ec = 0, e_ld = 0, e_math = 0, e_sts = 0, e_fence = 0;
+            // The residual tile stays in its ring slot and is read pass by pass, right where it is added (keeping all of
+            // it in registers from the start of the tile cost 32 registers per thread and pushed the epilogue into
+            // local-memory spills, which the ~28 KB of L1 left beside 227 KB of shared memory cannot hold).
+            stage = (stage + num_kb) % CS_STAGES;                            // ring position of the residual block, if any
+            uint32_t rs = 0;
             if (has_res) {
-                stage = (stage + num_kb) % CS_STAGES;
                 mbar_wait(&res_full[r_local & 1], (uint32_t)(r_local >> 1) & 1u);
-                const uint32_t rs = smem_u32(smem + stage * CS_STAGE_BYTES);
+                rs = smem_u32(smem + stage * CS_STAGE_BYTES);
+                if (prof) e_res = clock64() - e0;
+            }
+            if (prof) ec = clock64();
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            if (prof) e_tf = clock64() - ec;
+            tc_fence_after();
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    if (g < np) {
+            for (int g = 0; g < 2; ++g) {
+                if (g < np) {
+                    const int n = T.nt * bn + g * 64 + csub * 16;
+                    const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + g * 64 + csub * 16);
+                    uint32_t r0[16], r1[16];
+                    if (prof) ec = clock64();
+                    tmem_ld16(t_d0, r0);
+                    if (x3) tmem_ld16(t_d0 + bn, r1);
+                    // BatchNorm vectors of this thread's 16 channels: issued before the TMEM wait, their latency hides behind it
+                    float sc[16], sh[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(scale + n + q * 4));
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(shift + n + q * 4));
+                        sc[q * 4] = a4.x; sc[q * 4 + 1] = a4.y; sc[q * 4 + 2] = a4.z; sc[q * 4 + 3] = a4.w;
+                        sh[q * 4] = b4.x; sh[q * 4 + 1] = b4.y; sh[q * 4 + 2] = b4.z; sh[q * 4 + 3] = b4.w;
+                    }
+                    tmem_ld_wait();
+                    if (prof) { const long long c = clock64(); e_ld += c - ec; ec = c; }
+                    if (g == np - 1) {                  // last TMEM read of the tile: hand the accumulator stage back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    float v[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        float a = __uint_as_float(r0[k]);
+                        if (x3) a = fmaf(__uint_as_float(r1[k]), 1.0f / 2048.0f, a);
+                        v[k] = fmaf(a, sc[k], sh[k]);
+                    }
+                    if (has_res) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const uint4 h4 = lds128(rs + g * 2 * TC_BM * 128 + soff[q]);
@@ -290,108 +370,99 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
                             for (int u = 0; u < 4; ++u) {
                                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
                                 const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
-                                rf[g][q * 8 + u * 2 + 0] = fmaf(lf.x, 1.0f / 2048.0f, hf.x);
-                                rf[g][q * 8 + u * 2 + 1] = fmaf(lf.y, 1.0f / 2048.0f, hf.y);
+                                v[q * 8 + u * 2 + 0] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
+                                v[q * 8 + u * 2 + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
                             }
                         }
-                    }
-                }
-                fence_proxy_async();                    // generic-proxy reads done before the slot returns to TMA
-                group_bar(3, CS_EPI_WARPS * 32);
-                if (threadIdx.x == 64) mbar_arrive(&empty_bar[stage]);
-                stage = (stage + 1) % CS_STAGES;
-                ++r_local;
-            } else {
-                stage = (stage + num_kb) % CS_STAGES;
-            }
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                if (g < np) {
-                    const int n = T.nt * bn + g * 64 + csub * 16;
-                    const uint32_t t_d0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + g * 64 + csub * 16);
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(t_d0, r0);
-                    if (x3) tmem_ld16(t_d0 + bn, r1);
-                    tmem_ld_wait();
-                    if (g == np - 1) {                  // last TMEM read of the tile: hand the accumulator stage back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        // (the slot is handed back to the TMA producer by the store lane, once every warp has arrived on
+                        //  stg_full for the tile's last pass: those arrivals follow each warp's last read of the block and
+                        //  its fence.proxy.async — no 512-thread barrier in the middle of the arithmetic)
                     }
                     uint32_t oh[8], ol[8];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + n + q * 8));
-                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + n + q * 8 + 4));
-                        const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + n + q * 8));
-                        const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + n + q * 8 + 4));
-                        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                        float v[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            float a = __uint_as_float(r0[q * 8 + k]);
-                            if (x3) a = fmaf(__uint_as_float(r1[q * 8 + k]), 1.0f / 2048.0f, a);
-                            v[k] = fmaf(a, sc[k], sh[k]);
-                        }
-                        if (has_res) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) v[k] += rf[g][q * 8 + k];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float a = v[u * 2], b = v[u * 2 + 1];
-                            if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                            else { a = fmaxf(a, -65504.f); b = fmaxf(b, -65504.f); }
-                            a = fminf(a, 65504.f);                              // fp16 range guard
-                            b = fminf(b, 65504.f);
-                            const __half2 h = __floats2half2_rn(a, b);
-                            const float2 hf = __half22float2(h);
-                            oh[q * 4 + u] = *reinterpret_cast<const uint32_t*>(&h);
-                            sat |= sat_probe(oh[q * 4 + u]);
-                            ol[q * 4 + u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
-                        }
+                    for (int u = 0; u < 8; ++u) {
+                        const float a = fminf(fmaxf(v[u * 2], lo_clamp), 65504.f);
+                        const float b = fminf(fmaxf(v[u * 2 + 1], lo_clamp), 65504.f);
+                        const __half2 h = __floats2half2_rn(a, b);
+                        const float2 hf = __half22float2(h);
+                        oh[u] = *reinterpret_cast<const uint32_t*>(&h);
+                        sat |= sat_probe(oh[u]);
+                        ol[u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                     }
-                    mbar_wait(stg_empty, se_phase ^ 1);             // the previous half tile has left the staging buffer
-                    se_phase ^= 1;
+                    const int owner = t_cta & (CS_STORE_WARPS - 1);
+                    if (prof) { const long long c = clock64(); e_math += c - ec; ec = c; }
+                    if (prev_owner >= 0) mbar_wait(&stg_empty[prev_owner], (passes[prev_owner] - 1) & 1u);   // previous half tile has left
+                    if (prof) { const long long c = clock64(); e_stg += c - ec; ec = c; }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         sts128(stg_hi + soff[q], make_uint4(oh[q * 4], oh[q * 4 + 1], oh[q * 4 + 2], oh[q * 4 + 3]));
                         sts128(stg_lo + soff[q], make_uint4(ol[q * 4], ol[q * 4 + 1], ol[q * 4 + 2], ol[q * 4 + 3]));
                     }
+                    if (prof) { const long long c = clock64(); e_sts += c - ec; ec = c; }
                     fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA store
+                    if (prof) { const long long c = clock64(); e_fence += c - ec; ec = c; }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(stg_full);
+                    if (lane == 0) mbar_arrive(&stg_full[owner]);
+                    passes[owner] += 1;
+                    prev_owner = owner;
                 }
             }
+            if (has_res) { stage = (stage + 1) % CS_STAGES; ++r_local; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            ++t_cta;
+            if (prof) {
+                atomicAdd(P.prof + 128 + T.layer, (unsigned long long)e_res);
+                atomicAdd(P.prof + 192 + T.layer, (unsigned long long)e_tf);
+                atomicAdd(P.prof + 256 + T.layer, (unsigned long long)e_stg);
+                atomicAdd(P.prof + 320 + T.layer, (unsigned long long)(clock64() - e0));
+                atomicAdd(P.prof + 512 + T.layer, (unsigned long long)e_ld);
+                atomicAdd(P.prof + 576 + T.layer, (unsigned long long)e_math);
+                atomicAdd(P.prof + 640 + T.layer, (unsigned long long)e_sts);
+                atomicAdd(P.prof + 704 + T.layer, (unsigned long long)e_fence);
+            }
         }
         if (sat & 0x80008000u) atomicAdd(P.sat_count, 1ull);
     } else if (lane == 0) {
-        // ====================================== store thread ======================================
-        int cur = 0;
-        uint32_t sf_phase = 0;
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        // ====================================== store lanes ======================================
+        // Two store warps (one lane each): the first sends the even tiles of this CTA, the second the odd ones.  A tile may only be published once its writes have
+        // COMPLETED (cp.async.bulk.wait_group 0 — about a microsecond after the stores were issued); bulk groups belong to
+        // the issuing thread, so with one store thread that wait would sit between every two tiles' stores.  With two, the
+        // other lane sends the next tile meanwhile.  Each lane has its own full / empty barrier pair, so neither can fall
+        // more than one phase behind on a barrier it waits on.
+        const int me = warp - (2 + CS_EPI_WARPS);
+        int cur = 0, t_cta = 0, stage = 0;
+        uint32_t my_pass = 0;
+        long long t_prev = PROF ? clock64() : 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++t_cta) {
             int tiles_n;
             const CsTile T = cs_decode(P, tile, cur, tiles_n);
             const CsLayer* L = P.layers + T.layer;
-            const int bn = __ldg(&L->bn);
+            const int4 li = __ldg(reinterpret_cast<const int4*>(&L->bn));      // bn, tiles_n, num_kb, has_res
+            stage = (stage + li.z) % CS_STAGES;                                 // ring position of the residual block, if any
+            const int res_stage = stage;
+            if (li.w) stage = (stage + 1) % CS_STAGES;
+            if ((t_cta & (CS_STORE_WARPS - 1)) != me) continue;
+            const int bn = li.x;
             const int np = bn >> 6;
             for (int g = 0; g < np; ++g) {
-                mbar_wait(stg_full, sf_phase);
-                sf_phase ^= 1;
+                mbar_wait(&stg_full[me], my_pass & 1u);
+                ++my_pass;
+                if (li.w && g == np - 1) mbar_arrive(&empty_bar[res_stage]);    // every warp is past its last residual read
                 tma_store_2d(&L->o_hi, smem + CS_STG_OFF, T.nt * bn + g * 64, T.mt * TC_BM);
                 if (x3) tma_store_2d(&L->o_lo, smem + CS_STG_OFF + TC_BM * 128, T.nt * bn + g * 64, T.mt * TC_BM);
                 bulk_commit();
                 bulk_wait_read0();
-                mbar_arrive(stg_empty);
+                mbar_arrive(&stg_empty[me]);
             }
             // publish the tile: its writes must have COMPLETED (not merely been read out of shared memory)
             bulk_wait0();
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(P.done + (long long)T.layer * P.done_stride + T.mt) : "memory");
+            if (PROF) {
+                const long long now = clock64();
+                atomicAdd(P.prof + T.layer, (unsigned long long)(now - t_prev));
+                t_prev = now;
+            }
         }
     }
     tc_fence_before();
@@ -408,7 +479,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
 struct StackPlan {
     int B = 0, terms = 0;
     const void* in_hi = nullptr;
-    unsigned long long epoch = 0;
+    const void* arena = nullptr;
+    unsigned long long weights_version = 0;
     int total_tiles = 0, num_segs = 0, done_stride = 0;
     CsLayer* layers_dev = nullptr;
     CsSegment* segs_dev = nullptr;
@@ -421,6 +493,7 @@ struct StackState {
     std::vector<StackPlan> plans;
     unsigned long long clock = 0;
     bool attr_set = false;
+    unsigned long long* prof_dev = nullptr;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -587,31 +660,63 @@ int launch_conv_stack(ivosw_ctx* c, const SplitAct& in, int B, int terms, cudaSt
         c->stack_arena_cap = cap;
         for (StackPlan& p : S->plans) p.B = 0;          // every cached plan points into the old arena
     }
-    const unsigned long long alloc_epoch = current_alloc_epoch();
+    // a plan bakes in: the unit count, the input planes, the arena and the weight buffers (tensor maps)
     StackPlan* plan = nullptr;
     for (StackPlan& p : S->plans)
-        if (p.B == B && p.terms == terms && p.in_hi == in.hi && p.epoch == alloc_epoch) { plan = &p; break; }
+        if (p.B == B && p.terms == terms && p.in_hi == in.hi && p.arena == c->stack_arena.p &&
+            p.weights_version == c->assess_version) { plan = &p; break; }
     if (!plan) {
         if (c->capturing) { set_error("conv stack plan must be built outside graph capture"); return IVOSW_ERR_STATE; }
         if (S->plans.size() < 12) { S->plans.emplace_back(); plan = &S->plans.back(); }
         else plan = &*std::min_element(S->plans.begin(), S->plans.end(),
                                        [](const StackPlan& a, const StackPlan& b) { return a.stamp < b.stamp; });
         if ((rc = build_plan(c, *plan, B, terms, in, offs, cap))) { plan->B = 0; return rc; }
-        plan->epoch = alloc_epoch;
+        plan->arena = c->stack_arena.p; plan->weights_version = c->assess_version;
     }
     plan->stamp = ++S->clock;
     if (!S->attr_set) {
-        IVOSW_CUDA(cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+        IVOSW_CUDA(cudaFuncSetAttribute(conv_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+        IVOSW_CUDA(cudaFuncSetAttribute(conv_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
         S->attr_set = true;
     }
     IVOSW_CUDA(cudaMemsetAsync(plan->done_dev, 0, plan->done_bytes, s));
     CsParams P;
     P.layers = plan->layers_dev; P.segs = plan->segs_dev; P.num_segs = plan->num_segs; P.total_tiles = plan->total_tiles;
     P.done = plan->done_dev; P.done_stride = plan->done_stride; P.terms = terms; P.sat_count = c->sat_count;
+    P.prof = nullptr;
+    static const bool profile = env_int("IVOSW_STACK_PROFILE", 0) != 0;
+    if (profile && !c->capturing) {
+        if (!S->prof_dev) IVOSW_CUDA(cudaMalloc(&S->prof_dev, sizeof(unsigned long long) * 768));
+        IVOSW_CUDA(cudaMemsetAsync(S->prof_dev, 0, sizeof(unsigned long long) * 768, s));
+        P.prof = S->prof_dev;
+    }
     const int grid = std::min(plan->total_tiles, c->sm_count);
-    conv_stack_kernel<<<grid, CS_THREADS, CS_SMEM, s>>>(P);
+    if (P.prof) conv_stack_kernel<true><<<grid, CS_THREADS, CS_SMEM, s>>>(P);
+    else conv_stack_kernel<false><<<grid, CS_THREADS, CS_SMEM, s>>>(P);
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
+    if (P.prof) {       // measurement only: synchronous read-back and a table on stderr
+        unsigned long long h[768];
+        IVOSW_CUDA(cudaMemcpyAsync(h, S->prof_dev, sizeof h, cudaMemcpyDeviceToHost, s));
+        IVOSW_CUDA(cudaStreamSynchronize(s));
+        unsigned long long tot = 0, totw = 0;
+        for (int li = 0; li < nL; ++li) { tot += h[li]; totw += h[64 + li]; }
+        (void)tot;
+        fprintf(stderr, "conv_stack profile (B = %d, grid = %d): cycles per CTA, per layer\n"
+                        "  layer                          epilogue-total  = wait-res + wait-acc + wait-staging + work | mma: wait-operands wait-acc-free | dep-wait(lookahead)\n", B, grid);
+        double te = 0;
+        for (int li = 0; li < nL; ++li) {
+            const ConvLayer& Lh = c->layers[li];
+            const double e = (double)h[320 + li] / grid, r = (double)h[128 + li] / grid, t = (double)h[192 + li] / grid,
+                         g = (double)h[256 + li] / grid;
+            te += e;
+            fprintf(stderr, "  %2d %dx%d s%d %4d->%4d @%2d  %9.0f = %8.0f + %8.0f + %8.0f + %8.0f | %8.0f %8.0f | %8.0f || ldtm %7.0f math %7.0f sts %7.0f fence %7.0f\n", li, Lh.k, Lh.k,
+                    Lh.stride, Lh.cin, Lh.cout, Lh.out_hw, e, r, t, g, e - r - t - g, (double)h[384 + li] / grid,
+                    (double)h[448 + li] / grid, (double)h[64 + li] / grid, (double)h[512 + li] / grid, (double)h[576 + li] / grid,
+                    (double)h[640 + li] / grid, (double)h[704 + li] / grid);
+        }
+        fprintf(stderr, "  total epilogue-thread cycles per CTA %.0f, dependency wait %.0f\n", te, (double)totw / grid);
+    }
     if (out) *out = arena_view(c, offs[nL - 1], layer_out_bytes(c->layers[nL - 1]) * cap);
     if (stage_out) {
         int k = 0;

@@ -165,7 +165,8 @@ struct ivosw_ctx {
     int stack_arena_cap = 0;
     int chunk_cap_seen = 0;
     void* stack_state = nullptr;
-    bool stack_on = true;
+    bool stack_on = false;
+    unsigned long long assess_version = 0;   // bumped by every ivosw_assess_load
 
     // host-staged rounds
     ivosw::DeviceBuffer stage_frames, stage_probs, scores_all;

@@ -260,3 +260,43 @@ def test_out_of_memory_surfaces_as_runtime_error(eng):
     s = e.assess_forward(tf[:2], tp[:2])
     assert torch.isfinite(s).all()
     e.close()
+
+
+def test_stack_kernel_matches_per_layer_kernels():
+    """conv_stack.cu (IVOSW_STACK=1: all 52 layers in one persistent launch, tile-level dependencies) against the default
+    conv_tc.cu (one launch per layer): the tile arithmetic is the same, so scores must agree bit for bit — for several group schedules
+    (units per group in res2 / res3 / res4 / res5, including groups that leave a ragged tail), an odd unit count
+    (8x8 tiles that span two images, the second one missing), and on graph replay."""
+    from ivosw.engine import Engine
+    T, H, W, O = 7, 160, 288, 3                      # 21 units
+    all_F, all_P, annotated = synth.make_clip(33, T, H, W, O)
+    ann = synth.annotated_counts(annotated, T)
+    F_d, P_d = torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda()
+    keys = ("IVOSW_STACK", "IVOSW_STACK_G2", "IVOSW_STACK_G3", "IVOSW_STACK_G4", "IVOSW_STACK_G5")
+    saved = {k: os.environ.get(k) for k in keys}
+    res = []
+    try:
+        for cfg in ({}, {"IVOSW_STACK": "1"},
+                    {"IVOSW_STACK": "1", "IVOSW_STACK_G2": "2", "IVOSW_STACK_G3": "4", "IVOSW_STACK_G4": "6", "IVOSW_STACK_G5": "10"},
+                    {"IVOSW_STACK": "1", "IVOSW_STACK_G2": "0", "IVOSW_STACK_G3": "0"},
+                    {"IVOSW_STACK": "1", "IVOSW_STACK_G2": "5", "IVOSW_STACK_G3": "3"}):
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(cfg)
+            e = Engine(0, CONV_MODE)
+            e.load_assess(synth.assess_state_dict(0)); e.load_brain(synth.brain_state_dict(0))
+            for _ in range(3):                        # eager, capture, replay
+                res.append(e.round_device(F_d, P_d, ann, want_scores=True))
+            res.append(e.round_device(F_d[:5], P_d[:5], ann[:5], want_scores=True, want_action=False))   # 15 units (odd)
+            assert e.saturation_count() == 0
+            e.close()
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    for i, r in enumerate(res):
+        ref = res[3] if r["scores"].shape[0] == 5 else res[0]
+        np.testing.assert_array_equal(r["scores"], ref["scores"], err_msg="run %d" % i)
+        if r["next_frame"] is not None:
+            assert r["next_frame"] == res[0]["next_frame"]
