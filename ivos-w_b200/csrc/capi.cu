@@ -277,7 +277,7 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
             // tensor-core path: activations live as split-fp16 planes inside the same workspace buffers
                 const SplitAct t1 = split_view(c->actT1), t2 = split_view(c->actT2), ds = split_view(c->actDS);
                 const SplitAct outs[2] = {split_view(c->actX), split_view(c->actY)};
-                int flip = 0, stage_probe = 2;
+                int flip = 0, stage_probe = 2, fused_idx = 0;
                 for (size_t li = 0; li < c->layers.size(); ++li) {
                     const ConvLayer& L = c->layers[li];
                     if (L.first_of_block) {
@@ -285,11 +285,17 @@ static int assess_units(ivosw_ctx* c, UnitAddr ua, int n_units, int H, int W, fl
                     } else if (L.k == 3) {
                         if ((rc = launch_conv_tc(c, L, t1, nullptr, t2, B, terms, s))) return rc;
                     } else if (L.is_downsample) {
-                        if ((rc = launch_conv_tc(c, L, xs, nullptr, ds, B, terms, s))) return rc;
+                        // fused into the conv3 that follows (one GEMM over [t2 ; x]) unless IVOSW_FUSE_DS=0
+                        if (!c->fuse_ds && (rc = launch_conv_tc(c, L, xs, nullptr, ds, B, terms, s))) return rc;
                     } else {
-                        const SplitAct* res = L.residual == 2 ? &ds : &xs;
                         const SplitAct y = outs[flip];
-                        if ((rc = launch_conv_tc(c, L, t2, res, y, B, terms, s))) return rc;
+                        if (L.residual == 2 && c->fuse_ds) {
+                            if ((rc = launch_conv_tc(c, L, t2, nullptr, y, B, terms, s, &c->fused_tail[fused_idx], &xs))) return rc;
+                        } else {
+                            const SplitAct* res = L.residual == 2 ? &ds : &xs;
+                            if ((rc = launch_conv_tc(c, L, t2, res, y, B, terms, s))) return rc;
+                        }
+                        if (L.residual == 2) ++fused_idx;
                         xs = y;
                         flip ^= 1;
                         const bool stage_end_ = (li + 1 == c->layers.size()) ||
@@ -434,6 +440,7 @@ int ivosw_create(int device, int conv_mode, ivosw_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->chunk_cap = chunk_cap_default();
     { const char* g = getenv("IVOSW_GRAPHS"); c->graphs_on = !(g && atoi(g) == 0); }
+    { const char* g = getenv("IVOSW_FUSE_DS"); c->fuse_ds = !(g && atoi(g) == 0); }
     { const char* g = getenv("IVOSW_STACK"); c->stack_on = g && atoi(g) != 0; }   // 1: conv_stack.cu (one persistent launch) instead of one launch per layer
     c->layers = make_resnet50_layers();
     if (cudaMalloc(&c->sat_count, sizeof(unsigned long long)) != cudaSuccess ||
@@ -466,6 +473,12 @@ void ivosw_destroy(ivosw_ctx* c) {
     if (c->stem_shift) cudaFree(c->stem_shift);
     if (c->stem_wpack) cudaFree(c->stem_wpack);
     if (c->fc_w) cudaFree(c->fc_w);
+    for (FusedTail& F : c->fused_tail) {
+        if (F.w_hi) cudaFree(F.w_hi);
+        if (F.w_lo) cudaFree(F.w_lo);
+        if (F.scale) cudaFree(F.scale);
+        if (F.shift) cudaFree(F.shift);
+    }
     for (ConvLayer& L : c->layers) {
         if (L.w_f32) cudaFree(L.w_f32);
         if (L.scale) cudaFree(L.scale);
@@ -656,6 +669,46 @@ int ivosw_assess_load(ivosw_ctx* c, const float* blob, size_t n_floats) {
         if ((rc = upload(&L.shift, sh.data(), L.cout))) return rc;
         p += 4 * (size_t)L.cout;
     }
+    {   // conv3 + downsample of each stage's first bottleneck as one GEMM: [s3 W3 | sd Wd], shift b3 + bd (conv_tc.cu)
+        const float* q = blob + 6 + (size_t)64 * 196 + 256;
+        std::vector<const float*> wp(c->layers.size()), bnp(c->layers.size());
+        for (size_t li = 0; li < c->layers.size(); ++li) {
+            const ConvLayer& L = c->layers[li];
+            wp[li] = q; q += (size_t)L.cout * L.k * L.k * L.cin;
+            bnp[li] = q; q += 4 * (size_t)L.cout;
+        }
+        int fi = 0;
+        for (size_t li = 0; li < c->layers.size(); ++li) {
+            if (!c->layers[li].is_downsample) continue;
+            const ConvLayer& D = c->layers[li];
+            const ConvLayer& C3 = c->layers[li + 1];
+            FusedTail& F = c->fused_tail[fi++];
+            const int cout = C3.cout, k3 = C3.cin, kd = D.cin, kt = k3 + kd;
+            std::vector<float> sc3, sh3, scd, shd;
+            fold_bn(bnp[li + 1], bnp[li + 1] + cout, bnp[li + 1] + 2 * cout, bnp[li + 1] + 3 * cout, cout, sc3, sh3);
+            fold_bn(bnp[li], bnp[li] + cout, bnp[li] + 2 * cout, bnp[li] + 3 * cout, cout, scd, shd);
+            std::vector<__half> hi((size_t)cout * kt), lo((size_t)cout * kt);
+            std::vector<float> ones(cout, 1.0f), shf(cout);
+            for (int o = 0; o < cout; ++o) {
+                shf[o] = (float)((double)sh3[o] + (double)shd[o]);
+                for (int k = 0; k < kt; ++k) {
+                    const double w = k < k3 ? (double)sc3[o] * (double)wp[li + 1][(size_t)o * k3 + k]
+                                            : (double)scd[o] * (double)wp[li][(size_t)o * kd + (k - k3)];
+                    const float wf = (float)w;
+                    const __half h = __float2half_rn(wf);
+                    hi[(size_t)o * kt + k] = h;
+                    lo[(size_t)o * kt + k] = __float2half_rn((wf - __half2float(h)) * 2048.0f);
+                }
+            }
+            if (!F.w_hi) IVOSW_CUDA(cudaMalloc(&F.w_hi, hi.size() * sizeof(__half)));
+            if (!F.w_lo) IVOSW_CUDA(cudaMalloc(&F.w_lo, lo.size() * sizeof(__half)));
+            IVOSW_CUDA(cudaMemcpy(F.w_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+            IVOSW_CUDA(cudaMemcpy(F.w_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+            if ((rc = upload(&F.scale, ones.data(), cout))) return rc;
+            if ((rc = upload(&F.shift, shf.data(), cout))) return rc;
+            F.k_total = kt; F.cin2 = kd; F.in_hw2 = D.in_hw; F.stride2 = D.stride;
+        }
+    }
     if ((rc = upload(&c->fc_w, p, 2048))) return rc;
     c->fc_b = p[2048];
     c->assess_loaded = true;
@@ -774,11 +827,11 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
     if ((rc = ensure(c->stage_frames, sizeof(float) * (size_t)T * 3 * HW))) return rc;
     if ((rc = ensure(c->stage_probs, sizeof(float) * (size_t)T * (O + 1) * HW))) return rc;
     if (keep_scores && (rc = ensure(c->scores_all, sizeof(float) * (size_t)Tl * O))) return rc;
-    if ((rc = ensure(c->band_rows, sizeof(int2) * (size_t)T))) return rc;
+    if ((rc = ensure(c->band_rows, sizeof(int4) * (size_t)T))) return rc;
     if (c->pinned_rows_n < (size_t)T) {
         if (c->pinned_rows) cudaFreeHost(c->pinned_rows);
         c->pinned_rows = nullptr; c->pinned_rows_n = 0;
-        IVOSW_CUDA(cudaMallocHost((void**)&c->pinned_rows, sizeof(int2) * (size_t)T));
+        IVOSW_CUDA(cudaMallocHost((void**)&c->pinned_rows, sizeof(int4) * (size_t)T));
         c->pinned_rows_n = (size_t)T;
     }
     float* fs = (float*)c->stage_frames.p;
@@ -789,6 +842,7 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
     // round trip per chunk; queueing the next chunk's planes ahead of these rows instead delays the scoring pass by a
     // whole plane transfer and measured slower (12.1 vs 11.6 ms).
     const bool bands = !(getenv("IVOSW_E2E_BANDS") && atoi(getenv("IVOSW_E2E_BANDS")) == 0);
+    const bool cols = !(getenv("IVOSW_E2E_COLS") && atoi(getenv("IVOSW_E2E_COLS")) == 0);   // 0: whole rows of the band
     // the copy stream must not overtake work already queued on s that may still read the staging buffers
     IVOSW_CUDA(cudaEventRecord(ev_start, s));
     IVOSW_CUDA(cudaStreamWaitEvent(c->copy_stream, ev_start, 0));
@@ -811,9 +865,9 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
                     c1 - c0, 0};
         if ((r = launch_bbox(c, ua, (c1 - c0) * O, H, W, c->aux_stream, &c->band_min, &c->band_max))) return r;
         if ((r = launch_roi_rows(c, (const int2*)c->band_min.p, (const int2*)c->band_max.p, c1 - c0, O, H, W,
-                                 (int2*)c->band_rows.p + c0, c->aux_stream)))
+                                 (int4*)c->band_rows.p + c0, c->aux_stream)))
             return r;
-        IVOSW_CUDA(cudaMemcpyAsync(c->pinned_rows + c0, (int2*)c->band_rows.p + c0, sizeof(int2) * (size_t)(c1 - c0),
+        IVOSW_CUDA(cudaMemcpyAsync(c->pinned_rows + c0, (int4*)c->band_rows.p + c0, sizeof(int4) * (size_t)(c1 - c0),
                                    cudaMemcpyDeviceToHost, c->aux_stream));
         IVOSW_CUDA(cudaEventRecord(ev_b[ci], c->aux_stream));
         return IVOSW_OK;
@@ -830,13 +884,25 @@ static int score_range_from_host(ivosw_ctx* c, const float* frames_host, const f
         if (bands) {
             IVOSW_CUDA(cudaEventSynchronize(ev_b[ci]));
             for (int t = c0; t < c1; ++t) {
-                const int2 r = c->pinned_rows[t];
+                const int4 r = c->pinned_rows[t];           // first / last row, first / last column an ROI of this frame can touch
                 if (r.x > r.y) continue;
-                const size_t off = (size_t)t * 3 * HW + (size_t)r.x * W;
-                const size_t bytes = sizeof(float) * (size_t)(r.y - r.x + 1) * W;
-                IVOSW_CUDA(cudaMemcpy2DAsync(fs + off, sizeof(float) * HW, frames_host + off, sizeof(float) * HW, bytes, 3,
-                                             cudaMemcpyHostToDevice, c->copy_stream));
-                sent += 3 * (long long)bytes;
+                const int nrows = r.y - r.x + 1, ncols = r.w - r.z + 1;
+                if (cols && ncols * 8 < W * 7) {
+                    // the rectangle only: one strided copy per colour plane (rows of ncols floats, 128-byte aligned starts)
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const size_t off = ((size_t)t * 3 + ch) * HW + (size_t)r.x * W + r.z;
+                        IVOSW_CUDA(cudaMemcpy2DAsync(fs + off, sizeof(float) * W, frames_host + off, sizeof(float) * W,
+                                                     sizeof(float) * (size_t)ncols, (size_t)nrows, cudaMemcpyHostToDevice,
+                                                     c->copy_stream));
+                    }
+                    sent += 3ll * (long long)sizeof(float) * ncols * nrows;
+                } else {
+                    const size_t off = (size_t)t * 3 * HW + (size_t)r.x * W;
+                    const size_t bytes = sizeof(float) * (size_t)nrows * W;
+                    IVOSW_CUDA(cudaMemcpy2DAsync(fs + off, sizeof(float) * HW, frames_host + off, sizeof(float) * HW, bytes, 3,
+                                                 cudaMemcpyHostToDevice, c->copy_stream));
+                    sent += 3 * (long long)bytes;
+                }
             }
         } else {
             IVOSW_CUDA(cudaMemcpyAsync(fs + (size_t)c0 * 3 * HW, frames_host + (size_t)c0 * 3 * HW,

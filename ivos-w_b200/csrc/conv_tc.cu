@@ -32,7 +32,9 @@ namespace ivosw {
 
 struct TcParams {
     int M, Cout, Cin;
-    int num_taps, cin_blocks;     // K blocks = num_taps * cin_blocks
+    int num_taps, cin_blocks;     // K blocks = num_taps * cin_blocks ...
+    int num_kb;                   // ... unless two GEMMs share the accumulator (kb_split > 0): blocks [0, kb_split) read
+    int kb_split;                 //     the first activation tensor (tap 0), blocks [kb_split, num_kb) the second (tap 1)
     int out_hw;                   // OH == OW
     int tiles_m, tiles_n;
     int relu, terms;              // terms: 3 (split-fp16) or 1
@@ -76,6 +78,7 @@ struct TcSmem {
 
 struct TcMaps {
     CUtensorMap a_hi, a_lo, w_hi, w_lo;       // operands
+    CUtensorMap a2_hi, a2_lo;                 // second activation tensor of a fused pair (kb_split > 0)
     CUtensorMap r_hi, r_lo, o_hi, o_lo;       // residual in / output (STAGED epilogue only)
 };
 
@@ -95,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = P.tiles_m * P.tiles_n;
-    const int num_kb = P.num_taps * P.cin_blocks;
+    const int num_kb = P.num_kb;
     const bool x3 = P.terms == 3;
     constexpr uint32_t TMEM_COLS = 4 * BN;           // 2 accumulator stages x (D0, D1)
 
@@ -136,7 +139,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 const int n_img = m0 / pix_per_img;
                 const int h0 = (m0 - n_img * pix_per_img) / P.out_hw;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / P.cin_blocks, cb = kb - tap * P.cin_blocks;
+                    int tap, cb;
+                    const CUtensorMap* mh = &maps.a_hi;
+                    const CUtensorMap* ml = &maps.a_lo;
+                    if (P.kb_split > 0) {
+                        if (kb < P.kb_split) { tap = 0; cb = kb; }
+                        else { tap = 1; cb = kb - P.kb_split; mh = &maps.a2_hi; ml = &maps.a2_lo; }
+                    } else { tap = kb / P.cin_blocks; cb = kb - tap * P.cin_blocks; }
                     const TcTap tp = P.taps[tap];
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
@@ -147,10 +156,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     }
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     const int c0 = tp.c_add + cb * TC_BK;
-                    tma_load_5d(st, &maps.a_hi, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                    tma_load_5d(st, mh, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
                     tma_load_2d(st + 2 * S::A_BYTES, &maps.w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
                     if (x3) {
-                        tma_load_5d(st + S::A_BYTES, &maps.a_lo, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                        tma_load_5d(st + S::A_BYTES, ml, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
                         tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
                     }
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
@@ -551,21 +560,36 @@ static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P
     return IVOSW_OK;
 }
 
+static void fill_tap(TcTap& t, int oy, int ox, int stride, int cin) {
+    // input offset (oy, ox) of a tap relative to stride * out
+    if (stride == 1) {
+        t.c_add = 0; t.w_add = ox; t.p = 0; t.h_add = oy;
+    } else {                                        // ih = 2*oh + oy = 2*(oh + d) + parity
+        const int py = oy & 1, px = ox & 1;
+        t.p = py; t.h_add = (oy - py) / 2;
+        t.c_add = px * cin; t.w_add = (ox - px) / 2;
+    }
+}
+
+// One convolution layer — or, with `fuse` set, the tail of a bottleneck's first block as ONE GEMM:
+//     out = relu( bn3(conv3(in)) + bn_d(downsample(in2)) )  =  relu( [s3 W3 | sd Wd] [in ; in2] + (b3 + bd) )
+// (both 1x1; the BatchNorm scales are folded into the concatenated weight fuse->w_hi/w_lo, the shifts added; the
+// downsample output never exists in memory: one 537 MB write and one 537 MB read less in res2.0 alone).
 int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const SplitAct* residual, const SplitAct& out,
-                   int B, int terms, cudaStream_t s) {
+                   int B, int terms, cudaStream_t s, const FusedTail* fuse, const SplitAct* in2) {
     // 128-column tiles, unless they would leave more than half of the SMs without a tile (small unit batches: an 8-GPU
     // shard, the chunks of the host-buffer path): then 64-column tiles double the CTAs at work
     const long long m_tiles = ((long long)B * L.out_hw * L.out_hw + TC_BM - 1) / TC_BM;
     static const int narrow_below = getenv("IVOSW_NARROW_BELOW") ? atoi(getenv("IVOSW_NARROW_BELOW")) : -1;
     const long long narrow_limit = narrow_below >= 0 ? narrow_below : c->sm_count / 2;
     const int BN = (L.cout >= 128 && m_tiles * (L.cout / 128) > narrow_limit) ? 128 : 64;
-    const int K = L.k * L.k * L.cin;
-    // the 1x1 "expand" layers (conv3 and downsample: Cout = 4 * planes) move the most output/residual bytes
-    // Epilogue through the staging buffer + TMA stores: always for the expand layers, and for every other
-    // layer with at least two waves of tiles (coalesced stores beat the per-thread 16-byte ones by
-    // 3-40 us per layer; with fewer tiles the two-pass epilogue of the last tile is a longer tail than it saves)
-    const long long n_tiles = (((long long)B * L.out_hw * L.out_hw + TC_BM - 1) / TC_BM) * (L.cout / BN);
-    const bool staged = ((L.k == 1 && L.cout >= 256 && (residual != nullptr || L.is_downsample)) || n_tiles >= 2 * c->sm_count) &&
+    const int K = fuse ? fuse->k_total : L.k * L.k * L.cin;
+    // Epilogue through the staging buffer + TMA stores: always for the 1x1 "expand" layers (conv3 and downsample:
+    // Cout = 4 * planes, the most output / residual bytes), and for every other layer with at least two waves of tiles
+    // (coalesced stores beat the per-thread 16-byte ones by 3-40 us per layer; with fewer tiles the two-pass epilogue of
+    // the last tile is a longer tail than it saves)
+    const long long n_tiles = m_tiles * (L.cout / BN);
+    const bool staged = ((L.k == 1 && L.cout >= 256 && (residual != nullptr || L.is_downsample || fuse)) || n_tiles >= 2 * c->sm_count) &&
                         getenv("IVOSW_NO_STAGED_EPILOGUE") == nullptr;
     int rc;
     TcMaps maps;
@@ -575,8 +599,12 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     P.M = B * L.out_hw * L.out_hw;
     if ((rc = encode_act_map(&maps.a_hi, in.hi, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
     if ((rc = encode_act_map(&maps.a_lo, in.lo, B, L.in_hw, L.cin, L.stride, L.out_hw))) return rc;
-    if ((rc = encode_w_map(&maps.w_hi, L.w_hi, K, L.cout, BN))) return rc;
-    if ((rc = encode_w_map(&maps.w_lo, L.w_lo, K, L.cout, BN))) return rc;
+    if (fuse) {
+        if ((rc = encode_act_map(&maps.a2_hi, in2->hi, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
+        if ((rc = encode_act_map(&maps.a2_lo, in2->lo, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
+    }
+    if ((rc = encode_w_map(&maps.w_hi, fuse ? fuse->w_hi : L.w_hi, K, L.cout, BN))) return rc;
+    if ((rc = encode_w_map(&maps.w_lo, fuse ? fuse->w_lo : L.w_lo, K, L.cout, BN))) return rc;
     if (staged) {
         if ((rc = encode_out_map(&maps.o_hi, out.hi, P.M, L.cout))) return rc;
         if ((rc = encode_out_map(&maps.o_lo, out.lo, P.M, L.cout))) return rc;
@@ -587,31 +615,27 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     }
     P.Cout = L.cout; P.Cin = L.cin;
     P.num_taps = L.k * L.k; P.cin_blocks = L.cin / TC_BK;
+    P.num_kb = K / TC_BK; P.kb_split = fuse ? L.cin / TC_BK : 0;
     P.out_hw = L.out_hw;
     P.tiles_m = (P.M + TC_BM - 1) / TC_BM; P.tiles_n = L.cout / BN;
     P.relu = L.relu ? 1 : 0; P.terms = terms;
     { const char* e = getenv("IVOSW_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
-    P.scale = L.scale; P.shift = L.shift;
+    P.scale = fuse ? fuse->scale : L.scale; P.shift = fuse ? fuse->shift : L.shift;
     P.res_hi = residual ? residual->hi : nullptr; P.res_lo = residual ? residual->lo : nullptr;
     P.out_hi = out.hi; P.out_lo = out.lo;
     P.sat_count = c->sat_count;
-    for (int kh = 0; kh < L.k; ++kh)
-        for (int kw = 0; kw < L.k; ++kw) {
-            TcTap& t = P.taps[kh * L.k + kw];
-            const int oy = kh - L.pad, ox = kw - L.pad;     // input offset of this tap relative to stride * out
-            if (L.stride == 1) {
-                t.c_add = 0; t.w_add = ox; t.p = 0; t.h_add = oy;
-            } else {                                        // ih = 2*oh + oy = 2*(oh + d) + parity
-                const int py = oy & 1, px = ox & 1;
-                t.p = py; t.h_add = (oy - py) / 2;
-                t.c_add = px * L.cin; t.w_add = (ox - px) / 2;
-            }
-        }
+    if (fuse) {
+        fill_tap(P.taps[0], 0, 0, 1, L.cin);
+        fill_tap(P.taps[1], 0, 0, fuse->stride2, fuse->cin2);
+    } else {
+        for (int kh = 0; kh < L.k; ++kh)
+            for (int kw = 0; kw < L.k; ++kw) fill_tap(P.taps[kh * L.k + kw], kh - L.pad, kw - L.pad, L.stride, L.cin);
+    }
     if (staged) {
         if (BN == 64) return launch_tc_variant<64, 4, true>(c, maps, P, s);
         // one K block per tile (res2: Cin = 64): output/residual traffic is everything, two staging buffers
         // matter more than a third ring slot
-        if (P.num_taps * P.cin_blocks == 1 && getenv("IVOSW_NO_STAGED2") == nullptr) return launch_tc_variant<128, 2, true>(c, maps, P, s);
+        if (P.num_kb == 1 && getenv("IVOSW_NO_STAGED2") == nullptr) return launch_tc_variant<128, 2, true>(c, maps, P, s);
         return launch_tc_variant<128, 3, true>(c, maps, P, s);
     }
     return BN == 128 ? launch_tc_variant<128, 3, false>(c, maps, P, s) : launch_tc_variant<64, 4, false>(c, maps, P, s);

@@ -53,6 +53,17 @@ struct ConvLayer {
 
 std::vector<ConvLayer> make_resnet50_layers();
 
+// conv3 + downsample of a stage's first bottleneck as one GEMM (conv_tc.cu: launch_conv_tc with `fuse`): the concatenated,
+// BatchNorm-scaled weight [cout][cin3 + cin_d] as split-fp16 planes, scale = 1, shift = shift3 + shift_d.
+struct FusedTail {
+    __half* w_hi = nullptr;
+    __half* w_lo = nullptr;
+    float* scale = nullptr;
+    float* shift = nullptr;
+    int k_total = 0;
+    int cin2 = 0, in_hw2 = 0, stride2 = 1;      // the downsample branch's input geometry
+};
+
 // Where the inputs of scoring unit u = (object o, frame f) live: u = u0 + local index, f = u % nF,
 // o = u / nF.  One AssessNet.forward call is nF = B, obj_stride = 0; a whole round is nF = frames of
 // the shard with obj_stride = H*W walking over all_P[:, 1:].
@@ -118,6 +129,8 @@ struct ivosw_ctx {
     float* fc_w = nullptr;           // 2048
     float fc_b = 0.f;
     std::vector<ivosw::ConvLayer> layers;
+    ivosw::FusedTail fused_tail[4];         // res2.0 .. res5.0: conv3 + downsample as one GEMM
+    bool fuse_ds = true;                    // IVOSW_FUSE_DS=0: two kernels and a round trip of the downsample output
     // fp16 range guard: epilogue threads whose tile produced a value clamped to +-65504 (split-fp16 planes cannot hold
     // more) bump this device counter; ivosw_conv_saturation_count reads it.  0 on every in-range network.
     unsigned long long* sat_count = nullptr;
@@ -176,7 +189,7 @@ struct ivosw_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;     // row-range pre-pass of the host-buffer path
     ivosw::DeviceBuffer band_min, band_max, band_rows;
-    int2* pinned_rows = nullptr; size_t pinned_rows_n = 0;
+    int4* pinned_rows = nullptr; size_t pinned_rows_n = 0;
     long long last_h2d_bytes = 0;          // bytes the last host-buffer call actually sent
 };
 
@@ -192,7 +205,7 @@ void release(DeviceBuffer& b);
 // ---- roi.cu
 int launch_bbox(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, cudaStream_t s, DeviceBuffer* mn_buf = nullptr,
                 DeviceBuffer* mx_buf = nullptr);
-int launch_roi_rows(ivosw_ctx* c, const int2* mn, const int2* mx, int nF, int O, int H, int W, int2* rows, cudaStream_t s);
+int launch_roi_rows(ivosw_ctx* c, const int2* mn, const int2* mx, int nF, int O, int H, int W, int4* rows, cudaStream_t s);
 int launch_roi_sample(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, float* boxes_out, bool split,
                       cudaStream_t s);
 int launch_crop_merge(ivosw_ctx* c, float* out, int B, int use_lo, cudaStream_t s);
@@ -206,7 +219,7 @@ int launch_conv_simt(ivosw_ctx* c, const ConvLayer& L, const float* in, const fl
                      int B, cudaStream_t s);
 // ---- conv_tc.cu
 int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const SplitAct* residual, const SplitAct& out,
-                   int B, int terms, cudaStream_t s);
+                   int B, int terms, cudaStream_t s, const FusedTail* fuse = nullptr, const SplitAct* in2 = nullptr);
 int launch_split(ivosw_ctx* c, const float* in, const SplitAct& out, long long n, cudaStream_t s);
 int launch_merge(ivosw_ctx* c, const SplitAct& in, float* out, long long n, int use_lo, cudaStream_t s);
 // ---- conv_stack.cu

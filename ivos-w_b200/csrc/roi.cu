@@ -165,11 +165,13 @@ __device__ inline float roi_src_row(const float* th, int oy, int H) {
 // per frame takes the union over the frame's objects of [floor(iy(0)), floor(iy(255)) + 1], clipped to the image,
 // with the very arithmetic of the sampler (plus one row of slack each side).  rows[t] = (first, last); first > last
 // means no row of the frame is read (every ROI row falls outside the image).
+// The same for columns: rows[t] = (first row, last row, first column, last column); the column range is widened to
+// 128-byte boundaries (whole DMA bursts).
 __global__ void roi_rows_kernel(const int2* __restrict__ mn, const int2* __restrict__ mx, int nF, int O, int H, int W,
-                                int2* __restrict__ rows) {
+                                int4* __restrict__ rows) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nF) return;
-    int lo = H, hi = -1;
+    int lo = H, hi = -1, clo = W, chi = -1;
     for (int o = 0; o < O; ++o) {
         const int u = o * nF + t;                      // unit order of UnitAddr: u = object * nF + frame
         float r[4], th[4];
@@ -178,12 +180,22 @@ __global__ void roi_rows_kernel(const int2* __restrict__ mn, const int2* __restr
         const float a = roi_src_row(th, 0, H), b = roi_src_row(th, ROI - 1, H);
         int y0 = (int)floorf(fminf(a, b)) - 1, y1 = (int)floorf(fmaxf(a, b)) + 2;
         y0 = max(y0, 0); y1 = min(y1, H - 1);
-        if (y0 <= y1) { lo = min(lo, y0); hi = max(hi, y1); }
+        // source column of ROI column ox, exactly as roi_sample_kernel evaluates it
+        const float gx0 = __fadd_rn(__fmul_rn(th[0], lin256(0)), th[1]), gx1 = __fadd_rn(__fmul_rn(th[0], lin256(ROI - 1)), th[1]);
+        const float xa = __fmul_rn(__fmul_rn(__fadd_rn(gx0, 1.f), 0.5f), (float)(W - 1));
+        const float xb = __fmul_rn(__fmul_rn(__fadd_rn(gx1, 1.f), 0.5f), (float)(W - 1));
+        int x0 = (int)floorf(fminf(xa, xb)) - 1, x1 = (int)floorf(fmaxf(xa, xb)) + 2;
+        x0 = max(x0, 0); x1 = min(x1, W - 1);
+        if (y0 <= y1 && x0 <= x1) {
+            lo = min(lo, y0); hi = max(hi, y1);
+            clo = min(clo, x0); chi = max(chi, x1);
+        }
     }
-    rows[t] = make_int2(lo, hi);
+    if (lo <= hi) { clo = clo & ~31; chi = min(W - 1, chi | 31); }
+    rows[t] = make_int4(lo, hi, clo, chi);
 }
 
-int launch_roi_rows(ivosw_ctx* c, const int2* mn, const int2* mx, int nF, int O, int H, int W, int2* rows, cudaStream_t s) {
+int launch_roi_rows(ivosw_ctx* c, const int2* mn, const int2* mx, int nF, int O, int H, int W, int4* rows, cudaStream_t s) {
     roi_rows_kernel<<<(nF + 63) / 64, 64, 0, s>>>(mn, mx, nF, O, H, W, rows);
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());

@@ -272,11 +272,13 @@ def test_stack_kernel_matches_per_layer_kernels():
     all_F, all_P, annotated = synth.make_clip(33, T, H, W, O)
     ann = synth.annotated_counts(annotated, T)
     F_d, P_d = torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda()
-    keys = ("IVOSW_STACK", "IVOSW_STACK_G2", "IVOSW_STACK_G3", "IVOSW_STACK_G4", "IVOSW_STACK_G5")
+    keys = ("IVOSW_STACK", "IVOSW_STACK_G2", "IVOSW_STACK_G3", "IVOSW_STACK_G4", "IVOSW_STACK_G5", "IVOSW_FUSE_DS")
     saved = {k: os.environ.get(k) for k in keys}
     res = []
     try:
-        for cfg in ({}, {"IVOSW_STACK": "1"},
+        # (the per-layer reference runs with IVOSW_FUSE_DS=0: the default path evaluates conv3 + downsample of a stage's first
+        #  block as one GEMM with folded BatchNorm scales — same mathematics, different rounding; checked at the end)
+        for cfg in ({"IVOSW_FUSE_DS": "0"}, {"IVOSW_STACK": "1"},
                     {"IVOSW_STACK": "1", "IVOSW_STACK_G2": "2", "IVOSW_STACK_G3": "4", "IVOSW_STACK_G4": "6", "IVOSW_STACK_G5": "10"},
                     {"IVOSW_STACK": "1", "IVOSW_STACK_G2": "0", "IVOSW_STACK_G3": "0"},
                     {"IVOSW_STACK": "1", "IVOSW_STACK_G2": "5", "IVOSW_STACK_G3": "3"}):
@@ -300,3 +302,10 @@ def test_stack_kernel_matches_per_layer_kernels():
         np.testing.assert_array_equal(r["scores"], ref["scores"], err_msg="run %d" % i)
         if r["next_frame"] is not None:
             assert r["next_frame"] == res[0]["next_frame"]
+    # default path (fused conv3 + downsample tails): equal to the unfused arithmetic far inside the parity tolerance
+    e = Engine(0, CONV_MODE)
+    e.load_assess(synth.assess_state_dict(0)); e.load_brain(synth.brain_state_dict(0))
+    fused = e.round_device(F_d, P_d, ann, want_scores=True)
+    e.close()
+    assert float(np.abs(fused["scores"] - res[0]["scores"]).max()) < 2e-5
+    assert fused["next_frame"] == res[0]["next_frame"]
