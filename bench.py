@@ -294,6 +294,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(local_rank, args.conv_mode)
+    peer_gather = ivdist.setup_peer_gather(eng) if world > 1 else False
     assess_sd, brain_sd = synth.assess_state_dict(0), synth.brain_state_dict(0)
     eng.load_assess(assess_sd)
     eng.load_brain(brain_sd)
@@ -452,7 +453,9 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(4, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_NOTE.get(args.conv_mode, "f32"), "data": "synthetic",
         "config": {"workload": WORKLOAD, "conv_mode": args.conv_mode, "frames_per_gpu": b - a,
-                   "parallelism": "frame-shard x%d + 1 all-gather" % world if world > 1 else "single GPU",
+                   "parallelism": ("frame-shard x%d + one exchange of T float64 (%s)" %
+                                   (world, "own kernels over NVLink peer memory, csrc/gather.cu" if peer_gather else
+                                    "NCCL all-gather")) if world > 1 else "single GPU",
                    "l2": "inputs (630 MB per clip, 2 clips alternating) exceed the 126 MB L2",
                    "launch": "CUDA-graph replay of the round (captured on the 2nd call per clip)",
                    "stage_timing": "live in the timed region" if world == 1 else "separate pass of the same steps"},

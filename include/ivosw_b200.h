@@ -235,6 +235,47 @@ IVOSW_API int ivosw_manet_tail(ivosw_ctx* ctx, const float* logits_dev, int T, i
 IVOSW_API int ivosw_rough_roi(ivosw_ctx* ctx, const float* labels_dev, float* out_dev, int B, int h, int w,
                     int dist, void* stream);
 
+/* ---- AssessNet optimisation step (quality_assessment.py::train :240-269; BASELINE config C5) ---------------------
+ * ivosw_assess_train_begin   (re)starts training from a parameter blob in ivosw_assess_load's layout: parameters and
+ *                            BatchNorm buffers go to the device, gradients and SGD momentum buffers start at zero.
+ * ivosw_assess_train_step    one loop iteration on B samples (frames B x 3 x H x W, probabilities B x H x W, device; targets
+ *                            B fp32 = the J&F metric; valid B int32 = `union[n] > 0`): train-mode forward (batch statistics,
+ *                            running statistics updated), masked MSE, backward, gradients ACCUMULATED onto the previous
+ *                            steps' (the reference never zeroes them) and clamped to [-1, 1], SGD with momentum and weight
+ *                            decay (apply_update = 0: forward + backward only; the gradient of this step stays in the buffer
+ *                            ivosw_assess_train_grads returns — all-reduce it across ranks, then ivosw_assess_train_apply).  loss_host: the loss (NaN when no sample is valid: the reference
+ *                            `continue`s before backward); pred_host (nullable): B predictions.  Synchronises.
+ * ivosw_assess_train_export  parameters + BatchNorm buffers (blob layout, loads back with ivosw_assess_load) and / or the
+ *                            accumulated clamped gradients (same layout; non-parameter slots zero) to host memory.
+ * ivosw_assess_train_grads   device pointer to the CURRENT step's raw gradient (blob layout) for an all-reduce between
+ *                            ivosw_assess_train_step(apply_update = 0) calls of several ranks. */
+IVOSW_API int ivosw_assess_train_begin(ivosw_ctx* ctx, const float* blob_host, size_t n_floats);
+IVOSW_API int ivosw_assess_train_step(ivosw_ctx* ctx, const float* frames_dev, long long frame_stride_floats,
+                                      const float* prob_dev, long long prob_stride_floats, int B, int H, int W,
+                                      const float* targets_dev, const int* valid_dev, float lr, float momentum,
+                                      float weight_decay, int apply_update, float* loss_host, float* pred_host, void* stream);
+IVOSW_API int ivosw_assess_train_apply(ivosw_ctx* ctx, float lr, float momentum, float weight_decay, void* stream);
+IVOSW_API int ivosw_assess_train_export(ivosw_ctx* ctx, float* blob_host, float* grad_host, void* stream);
+IVOSW_API int ivosw_assess_train_grads(ivosw_ctx* ctx, float** grads_dev, size_t* n_floats);
+
+/* ---- the exchange step of the frame-sharded round over NVLink peer memory ----------------
+ * Instead of an NCCL all-gather of ceil(T / G) doubles per rank, every rank writes its slice of the per-frame quality
+ * vector straight into every rank's gather buffer (peer stores) and raises a flag there; Brain starts once all G flags
+ * of the local buffer carry the round's number.  Both are small kernels of this library on the caller's stream: no host
+ * synchronisation, no collective call, CUDA-graph capturable (csrc/gather.cu).
+ *   ivosw_gather_create  allocates this rank's buffer (capacity = largest T) and returns its 64-byte cudaIpcMemHandle_t
+ *   ivosw_gather_open    handles: world x 64 bytes, rank order (exchanged by the host framework, e.g. one all_gather at
+ *                        start-up); maps every peer buffer (cudaIpcOpenMemHandle, peer access enabled lazily)
+ *   ivosw_gather_post    after ivosw_score_shard(.., mq_dev = mq_local_dev ..): posts frames [offset, offset + n_local) of this
+ *                        round; EVERY rank calls it exactly once per round (n_local = 0 for an empty shard)
+ *   ivosw_agent_action_gathered  waits for all ranks' slices of the round, then Brain + argmax (as ivosw_agent_action_dev);
+ *                        mask_quality_host (nullable) receives the gathered T doubles.  Synchronises the stream. */
+IVOSW_API int ivosw_gather_create(ivosw_ctx* ctx, int world, int rank, int capacity, void* handle_out /*64 bytes*/);
+IVOSW_API int ivosw_gather_open(ivosw_ctx* ctx, const void* handles /*world x 64 bytes*/);
+IVOSW_API int ivosw_gather_post(ivosw_ctx* ctx, const double* mq_local_dev, int n_local, int offset, void* stream);
+IVOSW_API int ivosw_agent_action_gathered(ivosw_ctx* ctx, const double* annotated_counts_host, int T, float* q_host,
+                                          int* next_frame, double* mask_quality_host, void* stream);
+
 /* ---- ATNet round wrapper glue (utils/utils_atnet.py::run_VOS_singleiact; config C3) -------------
  * The ATNet networks are external (yuk6heo/IVOS-ATNet, not in the reference tree); these are the wrapper's own
  * element-wise passes, each one kernel:

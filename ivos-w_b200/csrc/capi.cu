@@ -467,6 +467,8 @@ void ivosw_destroy(ivosw_ctx* c) {
     release(c->dqn_ws);
     if (c->sat_count) cudaFree(c->sat_count);
     conv_stack_release(c);
+    gather_release(c);
+    train_release(c);
     release(c->stack_arena);
     if (c->stem_w) cudaFree(c->stem_w);
     if (c->stem_scale) cudaFree(c->stem_scale);
@@ -1174,6 +1176,111 @@ int ivosw_dqn_set_optimizer(ivosw_ctx* c, const float* m_dev, const float* v_dev
     IVOSW_CUDA(cudaMemcpyAsync(c->adam_m, m_dev, nb, cudaMemcpyDeviceToDevice, s));
     IVOSW_CUDA(cudaMemcpyAsync(c->adam_v, v_dev, nb, cudaMemcpyDeviceToDevice, s));
     c->adam_step = step;
+    return IVOSW_OK;
+}
+
+// ---------------------------------------------------------------- AssessNet training step (config C5)
+int ivosw_assess_train_begin(ivosw_ctx* c, const float* blob, size_t n_floats) {
+    IVOSW_REQUIRE(c && blob, "null pointer");
+    IVOSW_REQUIRE(n_floats == assess_blob_floats(), "AssessNet blob length");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < 3; ++i) { c->mean[i] = blob[i]; c->stdv[i] = blob[3 + i]; }
+    return train_begin(c, blob, n_floats);
+}
+
+int ivosw_assess_train_step(ivosw_ctx* c, const float* frames_dev, long long frame_stride, const float* prob_dev,
+                            long long prob_stride, int B, int H, int W, const float* targets_dev, const int* valid_dev,
+                            float lr, float momentum, float weight_decay, int apply_update, float* loss_host,
+                            float* pred_host, void* stream) {
+    IVOSW_REQUIRE(c && frames_dev && prob_dev && targets_dev && valid_dev, "null pointer");
+    IVOSW_REQUIRE(B >= 1 && H >= 2 && W >= 2, "B, H, W");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c->boxes, (size_t)B * 4 * sizeof(float)))) return rc;
+    UnitAddr ua{frames_dev, frame_stride, prob_dev, prob_stride, 0, B, 0};
+    return train_step(c, ua, B, H, W, targets_dev, valid_dev, lr, momentum, weight_decay, apply_update, loss_host, pred_host,
+                      (cudaStream_t)stream);
+}
+
+int ivosw_assess_train_apply(ivosw_ctx* c, float lr, float momentum, float weight_decay, void* stream) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    int rc = train_apply(c, lr, momentum, weight_decay, (cudaStream_t)stream);
+    if (rc) return rc;
+    IVOSW_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return IVOSW_OK;
+}
+
+int ivosw_assess_train_export(ivosw_ctx* c, float* blob_host, float* grad_host, void* stream) {
+    IVOSW_REQUIRE(c != nullptr, "ctx");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return train_export(c, blob_host, grad_host, (cudaStream_t)stream);
+}
+
+int ivosw_assess_train_grads(ivosw_ctx* c, float** grads_dev, size_t* n_floats) {
+    IVOSW_REQUIRE(c && grads_dev && n_floats, "null pointer");
+    return train_grad_buffer(c, grads_dev, n_floats);
+}
+
+// ---------------------------------------------------------------- peer-memory gather (multi-GPU round)
+int ivosw_gather_create(ivosw_ctx* c, int world, int rank, int capacity, void* handle_out) {
+    IVOSW_REQUIRE(c && handle_out, "null pointer");
+    IVOSW_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && capacity >= 1, "world (<= 64), rank, capacity");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return gather_create(c, world, rank, capacity, handle_out);
+}
+
+int ivosw_gather_open(ivosw_ctx* c, const void* handles) {
+    IVOSW_REQUIRE(c && handles, "null pointer");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return gather_open(c, handles);
+}
+
+int ivosw_gather_post(ivosw_ctx* c, const double* mq_local_dev, int n_local, int offset, void* stream) {
+    IVOSW_REQUIRE(c && (mq_local_dev || n_local == 0), "null pointer");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return gather_post(c, mq_local_dev, n_local, offset, (cudaStream_t)stream);
+}
+
+int ivosw_agent_action_gathered(ivosw_ctx* c, const double* ann_host, int T, float* q_host, int* next_frame, double* mq_host,
+                                void* stream) {
+    IVOSW_REQUIRE(c && ann_host, "null pointer");
+    IVOSW_REQUIRE(T >= 1, "T");
+    if (!c->brain_loaded) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure(c->mq, sizeof(double) * 2 * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_state, sizeof(float) * 2 * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_q, sizeof(float) * (size_t)T))) return rc;
+    if ((rc = ensure(c->brain_arg, sizeof(int)))) return rc;
+    if ((rc = ensure(c->brain_gi, sizeof(float) * (size_t)T * 512))) return rc;
+    if ((rc = ensure(c->brain_h, sizeof(float) * (size_t)2 * T * 128))) return rc;
+    if ((rc = ensure_pinned(c, sizeof(double) * 2 * T + sizeof(float) * T + 64))) return rc;
+    double* pin_ann = (double*)c->pinned_small;
+    double* pin_mq = pin_ann + T;
+    float* pin_q = (float*)(pin_mq + T);
+    int* pin_arg = (int*)(pin_q + T);
+    double* mq_dev = (double*)c->mq.p;        // gathered vector, copied out of the gather buffer for the caller
+    double* ann_dev = mq_dev + T;
+    memcpy(pin_ann, ann_host, sizeof(double) * T);
+    auto enqueue = [&](cudaStream_t st) -> int {
+        int r;
+        IVOSW_CUDA(cudaMemcpyAsync(ann_dev, pin_ann, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+        if ((r = gather_wait_pack(c, ann_dev, T, (float*)c->brain_state.p, mq_dev, st))) return r;
+        if ((r = timed_brain(c, T, st))) return r;
+        IVOSW_CUDA(cudaMemcpyAsync(pin_q, c->brain_q.p, sizeof(float) * T, cudaMemcpyDeviceToHost, st));
+        IVOSW_CUDA(cudaMemcpyAsync(pin_arg, c->brain_arg.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        IVOSW_CUDA(cudaMemcpyAsync(pin_mq, mq_dev, sizeof(double) * T, cudaMemcpyDeviceToHost, st));
+        return IVOSW_OK;
+    };
+    ivosw_ctx::GraphKey key{c->gather_state, nullptr, nullptr, T, 0, 0, 0, 0, 0, 0, 6, 0};
+    if ((rc = run_graphed(c, key, s, enqueue))) return rc;
+    IVOSW_CUDA(cudaStreamSynchronize(s));
+    drain_graph_events(c);
+    if (q_host) memcpy(q_host, pin_q, sizeof(float) * T);
+    if (next_frame) *next_frame = *pin_arg;
+    if (mq_host) memcpy(mq_host, pin_mq, sizeof(double) * T);
     return IVOSW_OK;
 }
 

@@ -113,6 +113,23 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
     }
 }
 
+// the same kernel with explicit operands (train.cu: raw convolutions, data gradients as convolutions)
+int launch_conv_simt_raw(ivosw_ctx* c, const float* in, const float* wgt, const float* scale, const float* shift,
+                         const float* residual, float* out, int B, int in_hw, int cin, int out_hw, int cout, int k, int stride,
+                         int pad, int relu, cudaStream_t s) {
+    if (cin % 16 != 0 || cout % 64 != 0) { set_error("conv_simt: Cin % 16 == 0 and Cout % 64 == 0 required"); return IVOSW_ERR_INVALID; }
+    ConvGeom g;
+    g.B = B; g.H = in_hw; g.W = in_hw; g.Cin = cin; g.OH = out_hw; g.OW = out_hw; g.Cout = cout;
+    g.k = k; g.stride = stride; g.pad = pad;
+    g.M = (long long)B * g.OH * g.OW;
+    g.K = k * k * cin;
+    dim3 grid((unsigned)((g.M + SM_BM - 1) / SM_BM), cout / SM_BN);
+    conv_simt_kernel<<<grid, 256, 0, s>>>(in, wgt, scale, shift, residual, out, g, relu);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
 int launch_conv_simt(ivosw_ctx* c, const ConvLayer& L, const float* in, const float* residual, float* out, int B,
                      cudaStream_t s) {
     ConvGeom g;

@@ -178,6 +178,8 @@ struct ivosw_ctx {
     int stack_arena_cap = 0;
     int chunk_cap_seen = 0;
     void* stack_state = nullptr;
+    void* train_state = nullptr;             // train.cu
+    void* gather_state = nullptr;            // gather.cu: peer-memory exchange of the frame-sharded round
     bool stack_on = false;
     unsigned long long assess_version = 0;   // bumped by every ivosw_assess_load
 
@@ -222,6 +224,20 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
                    int B, int terms, cudaStream_t s, const FusedTail* fuse = nullptr, const SplitAct* in2 = nullptr);
 int launch_split(ivosw_ctx* c, const float* in, const SplitAct& out, long long n, cudaStream_t s);
 int launch_merge(ivosw_ctx* c, const SplitAct& in, float* out, long long n, int use_lo, cudaStream_t s);
+// ---- train.cu (AssessNet optimisation step, config C5)
+int train_begin(ivosw_ctx* c, const float* blob, size_t n_floats);
+int train_step(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, const float* targets_dev, const int* valid_dev, float lr,
+               float momentum, float wd, int apply, float* loss_host, float* pred_host, cudaStream_t s);
+int train_apply(ivosw_ctx* c, float lr, float momentum, float wd, cudaStream_t s);
+int train_export(ivosw_ctx* c, float* blob_host, float* grad_host, cudaStream_t s);
+int train_grad_buffer(ivosw_ctx* c, float** gnew_dev, size_t* n);
+void train_release(ivosw_ctx* c);
+// ---- gather.cu
+int gather_create(ivosw_ctx* c, int world, int rank, int cap, void* handle_out);
+int gather_open(ivosw_ctx* c, const void* handles);
+int gather_post(ivosw_ctx* c, const double* mq_local_dev, int n_local, int offset, cudaStream_t s);
+int gather_wait_pack(ivosw_ctx* c, const double* ann_dev, int T, float* state_dev, double* mq_out_dev, cudaStream_t s);
+void gather_release(ivosw_ctx* c);
 // ---- conv_stack.cu
 int launch_conv_stack(ivosw_ctx* c, const SplitAct& in, int B, int terms, cudaStream_t s, SplitAct* out, SplitAct* stage_out);
 void conv_stack_release(ivosw_ctx* c);

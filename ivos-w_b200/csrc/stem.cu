@@ -18,7 +18,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float4* __restrict
                                                         const float* __restrict__ wgt,    // [196][64]
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ shift,
-                                                        float* __restrict__ c1) {         // [B][128][128][64]
+                                                        float* __restrict__ c1,           // [B][128][128][64]
+                                                        int raw) {                        // 1: convolution only (training)
     extern __shared__ float smem[];
     float* sw = smem;                       // 196 * 64
     float4* sp = reinterpret_cast<float4*>(smem + ST_K * 64);  // 21 * 37 float4
@@ -60,15 +61,16 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float4* __restrict
             }
         }
     }
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
+    const float4 sc = raw ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldg(reinterpret_cast<const float4*>(scale) + cg);
+    const float4 sh = raw ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(shift) + cg);
+    const float floor_ = raw ? -INFINITY : 0.f;
 #pragma unroll
     for (int r = 0; r < ST_TH; ++r) {
         float4 o;
-        o.x = fmaxf(fmaf(acc[r][0], sc.x, sh.x), 0.f);
-        o.y = fmaxf(fmaf(acc[r][1], sc.y, sh.y), 0.f);
-        o.z = fmaxf(fmaf(acc[r][2], sc.z, sh.z), 0.f);
-        o.w = fmaxf(fmaf(acc[r][3], sc.w, sh.w), 0.f);
+        o.x = fmaxf(fmaf(acc[r][0], sc.x, sh.x), floor_);
+        o.y = fmaxf(fmaf(acc[r][1], sc.y, sh.y), floor_);
+        o.z = fmaxf(fmaf(acc[r][2], sc.z, sh.z), floor_);
+        o.w = fmaxf(fmaf(acc[r][3], sc.w, sh.w), floor_);
         long long pix = ((long long)b * 128 + (oy0 + r)) * 128 + (ox0 + px);
         reinterpret_cast<float4*>(c1 + pix * 64)[cg] = o;
     }
@@ -100,17 +102,35 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float4* __restrict__
     out[i] = m;
 }
 
-int launch_stem(ivosw_ctx* c, int B, cudaStream_t s) {
-    const size_t smem = (size_t)ST_K * 64 * 4 + (size_t)ST_PH * ST_PW * 16;
+static int stem_attr(ivosw_ctx* c, size_t smem) {
     static bool attr_set[64] = {};          // per device (the attribute is not process-wide)
     const int dv = c->device & 63;
     if (!attr_set[dv]) {
         IVOSW_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dv] = true;
     }
+    return IVOSW_OK;
+}
+
+// the 4-channel 7x7/2 convolution alone, on explicit operands (train.cu): crop [B][256][256][4], wgt [196][64]
+int launch_stem_conv_raw(ivosw_ctx* c, const float* crop, const float* wgt_kc, float* out, int B, cudaStream_t s) {
+    const size_t smem = (size_t)ST_K * 64 * 4 + (size_t)ST_PH * ST_PW * 16;
+    int rc;
+    if ((rc = stem_attr(c, smem))) return rc;
+    dim3 grid(128 / ST_TW, 128 / ST_TH, B);
+    stem_conv_kernel<<<grid, 256, smem, s>>>((const float4*)crop, wgt_kc, nullptr, nullptr, out, 1);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
+int launch_stem(ivosw_ctx* c, int B, cudaStream_t s) {
+    const size_t smem = (size_t)ST_K * 64 * 4 + (size_t)ST_PH * ST_PW * 16;
+    int rc;
+    if ((rc = stem_attr(c, smem))) return rc;
     dim3 grid(128 / ST_TW, 128 / ST_TH, B);
     stem_conv_kernel<<<grid, 256, smem, s>>>((const float4*)c->crop.p, c->stem_w, c->stem_scale, c->stem_shift,
-                                             (float*)c->c1.p);
+                                             (float*)c->c1.p, 0);
     IVOSW_CUDA(cudaGetLastError());
     long long total = (long long)B * 64 * 64 * 16;
     maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float4*)c->c1.p, (float4*)c->pool.p, total);

@@ -129,6 +129,7 @@ struct Params {
     int n_items;               // B * bands
     int bands;                 // row bands per image
     int terms;                 // 3 or 1
+    unsigned long long* sat_count;   // fp16 range guard events (ivosw_conv_saturation_count)
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
                             const __half2 h = __floats2half2_rn(a, b);
                             const float2 hf = __half22float2(h);
                             oh_[k >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                            if (((oh_[k >> 1] & 0x7FFF7FFFu) + 0x04010401u) & 0x80008000u) atomicAdd(P.sat_count, 1ull);   // clamped to 65504
                             ol_[k >> 1] = pack2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                         }
                         const size_t off = (((size_t)img * 64 + p) * 64 + q) * 64 + cq * 16;
@@ -391,6 +393,7 @@ int launch_stem_tc(ivosw_ctx* c, int B, const SplitAct& out, int terms, cudaStre
     P.scale = c->stem_scale; P.shift = c->stem_shift;
     P.out_hi = out.hi; P.out_lo = out.lo;
     P.bands = best; P.n_items = B * best; P.terms = terms;
+    P.sat_count = c->sat_count;
     const int grid = P.n_items < c->sm_count ? P.n_items : c->sm_count;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_TOTAL; cfg.stream = s;

@@ -60,6 +60,17 @@ SYMBOLS = {
     "ivosw_stage_times": (C.c_int, [C.c_void_p, _c_f, C.POINTER(C.c_longlong), C.c_int]),
     "ivosw_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_i,
                                    C.c_void_p]),
+    "ivosw_assess_train_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ivosw_assess_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, _c_f,
+                                          C.c_void_p, C.c_void_p]),
+    "ivosw_assess_train_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "ivosw_assess_train_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ivosw_assess_train_grads": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "ivosw_gather_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ivosw_gather_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ivosw_gather_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ivosw_agent_action_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, _c_i, C.c_void_p, C.c_void_p]),
     "ivosw_atnet_reflect_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_void_p]),
     "ivosw_atnet_sigmoid_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,

@@ -2,12 +2,21 @@
 
 One process per GPU (``torch.distributed``, NCCL over NVLink; gloo on CPU for the
 host-logic tests).  Rank r owns the contiguous frame range ``shard_range(T, G, r)``
-and scores it for every object; ONE all-gather of the per-frame float64 mean
-quality follows — the Q-network is a bidirectional LSTM over all frames, so the
-gather must precede it — and every rank then runs Brain + argmax redundantly on
-the identical vector (deterministic kernel -> identical index on every rank).
-No other collective is on the path.
+and scores it for every object; ONE exchange of the per-frame float64 mean quality
+follows — the Q-network is a bidirectional LSTM over all frames, so the gather
+must precede it — and every rank then runs Brain + argmax redundantly on the
+identical vector (deterministic kernel -> identical index on every rank).
+
+The exchange: after ``setup_peer_gather`` (one start-up all_gather of 64-byte IPC
+handles through torch.distributed) it is two small kernels of the CUDA library that
+write each rank's slice straight into every rank's buffer over NVLink peer memory
+and wait on flags there (csrc/gather.cu) — no collective call and no host
+synchronisation on the critical path.  Without it (or with ``IVOSW_PEER_GATHER=0``)
+the same bytes go through ``all_gather_into_tensor`` (NCCL), which is also what the
+gloo tests of the protocol use.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -26,6 +35,21 @@ def gather_layout(T, world):
     return per, per * world
 
 
+def setup_peer_gather(engine, group=None, capacity=1024):
+    """Start-up, once per process: allocate this rank's gather buffer, exchange the IPC handles, map the peers.
+    Returns True when the peer path is active (CUDA engine, world > 1, not disabled)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1 or os.environ.get("IVOSW_PEER_GATHER", "1") == "0":
+        return False
+    mine = torch.frombuffer(bytearray(engine.gather_create(world, rank, capacity)), dtype=torch.uint8).to(engine.device)
+    allh = torch.empty(64 * world, dtype=torch.uint8, device=engine.device)
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    engine.gather_open(bytes(allh.cpu().numpy().tobytes()))
+    dist.barrier(group)
+    return True
+
+
 def sharded_round(engine, all_F, all_P, annotated_counts, group=None):
     """all_F / all_P: this rank's FULL-clip tensors are not needed — only rows [a, b) are read, so callers
     may pass tensors whose other rows are uninitialised.  Returns (next_frame, q[T], mask_quality[T])."""
@@ -34,6 +58,17 @@ def sharded_round(engine, all_F, all_P, annotated_counts, group=None):
     T = all_F.shape[0]
     per, padded = gather_layout(T, world)
     a, b = shard_range(T, world, rank)
+    if engine.gather_ready:
+        # peer-memory exchange: score into a local vector, post it into every rank's buffer, wait for all slices + Brain
+        local = _local_mq(engine, per)
+        if b > a:
+            if all_F.is_cuda:
+                engine.score_shard(all_F, all_P, a, b, local[: b - a])
+            else:
+                engine.score_shard_host(all_F, all_P, a, b, local[: b - a])
+        engine.gather_post(local[: b - a] if b > a else None, a)
+        nf, q, mq = engine.agent_action_gathered(annotated_counts)
+        return nf, q, torch.from_numpy(mq)
     buf = torch.zeros(padded, dtype=torch.float64, device=engine.device)
     if b > a:
         if all_F.is_cuda:
@@ -44,6 +79,18 @@ def sharded_round(engine, all_F, all_P, annotated_counts, group=None):
         dist.all_gather_into_tensor(buf, buf[rank * per:(rank + 1) * per].clone(), group=group)
     nf, q = engine.agent_action_dev(buf[:T], annotated_counts)
     return nf, q, buf[:T]
+
+
+_LOCAL_MQ = {}
+
+
+def _local_mq(engine, per):
+    """Stable per-engine scratch for this rank's slice (a stable address keeps the CUDA-graph replay of score_shard)."""
+    t = _LOCAL_MQ.get(id(engine))
+    if t is None or t.numel() < per:
+        t = torch.zeros(max(per, 64), dtype=torch.float64, device=engine.device)
+        _LOCAL_MQ[id(engine)] = t
+    return t
 
 
 def host_gather_round(local_mq, T, annotated_counts, action_fn, group=None):

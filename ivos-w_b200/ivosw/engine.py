@@ -54,6 +54,35 @@ def pack_assess(sd):
     return out
 
 
+def unpack_assess(blob, template, grads=False):
+    """Inverse of pack_assess: flat blob -> dict with the reference's key names (OHWI -> OIHW).  Keys the blob does not
+    carry (conv1_m / conv1_n, num_batches_tracked) are taken from ``template`` (gradients: omitted)."""
+    out = {} if grads else {k: v.clone() for k, v in template.items()}
+    o = 6
+    if not grads:
+        out["Encoder.mean"] = torch.from_numpy(blob[0:3].copy()).view(1, 3, 1, 1)
+        out["Encoder.std"] = torch.from_numpy(blob[3:6].copy()).view(1, 3, 1, 1)
+    stem = torch.from_numpy(blob[o:o + 64 * 196].copy()).view(64, 7, 7, 4).permute(0, 3, 1, 2).contiguous()
+    out["Encoder.conv1.weight"], out["Encoder.conv1_p.weight"] = stem[:, :3].contiguous(), stem[:, 3:].contiguous()
+    o += 64 * 196
+    names = ("weight", "bias") if grads else ("weight", "bias", "running_mean", "running_var")
+    for j, s_ in enumerate(("weight", "bias", "running_mean", "running_var")):
+        if s_ in names:
+            out["Encoder.bn1." + s_] = torch.from_numpy(blob[o + 64 * j:o + 64 * (j + 1)].copy())
+    o += 256
+    for c in arch.resnet50_convs():
+        n = c.cout * c.k * c.k * c.cin
+        out[c.name + ".weight"] = torch.from_numpy(blob[o:o + n].copy()).view(c.cout, c.k, c.k, c.cin).permute(0, 3, 1, 2).contiguous()
+        o += n
+        for j, s_ in enumerate(("weight", "bias", "running_mean", "running_var")):
+            if s_ in names:
+                out[c.bn + "." + s_] = torch.from_numpy(blob[o + c.cout * j:o + c.cout * (j + 1)].copy())
+        o += 4 * c.cout
+    out["fc1.weight"] = torch.from_numpy(blob[o:o + 2048].copy()).view(1, 2048)
+    out["fc1.bias"] = torch.from_numpy(blob[o + 2048:o + 2049].copy())
+    return out
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -313,6 +342,85 @@ class Engine:
         check(lib.ivosw_agent_action_dev(self._h, _ptr(mq_dev), _np_ptr(ann), T, _np_ptr(q), C.byref(nf),
                                          _stream(self.device)))
         return int(nf.value), q
+
+    # ------------------------------------------------------------------ AssessNet training step (csrc/train.cu, config C5)
+    def train_begin(self, sd):
+        """(Re)start training from an AssessNet state dict (reference key names): quality_assessment.py:300-312."""
+        blob = pack_assess(sd)
+        check(lib.ivosw_assess_train_begin(self._h, _np_ptr(blob), blob.size))
+        self._train_template = {k: v.clone() for k, v in sd.items()}
+
+    def train_step(self, imgs, probs, targets, valid, lr=5e-6, momentum=0.9, weight_decay=5e-4, apply=True):
+        """One iteration of quality_assessment.py::train's loop body (:240-269).  imgs B x 3 x H x W, probs B x H x W,
+        targets B, valid B (bool: `union[n] > 0`).  Returns (loss or None when no sample is valid, pred B numpy)."""
+        tf = self._dev32(imgs)
+        B, _, H, W = tf.shape
+        tp = self._dev32(probs)
+        tg = self._dev32(torch.as_tensor(targets).reshape(-1))
+        vd = torch.as_tensor(np.asarray(valid)).to(self.device, torch.int32).contiguous()
+        loss = C.c_float(0.0)
+        pred = np.empty(B, dtype=np.float32)
+        check(lib.ivosw_assess_train_step(self._h, _ptr(tf), 3 * H * W, _ptr(tp), H * W, B, H, W, _ptr(tg), _ptr(vd), lr, momentum,
+                                          weight_decay, 1 if apply else 0, C.byref(loss), _np_ptr(pred), _stream(self.device)))
+        lv = float(loss.value)
+        return (None if lv != lv else lv), pred
+
+    def train_apply(self, lr=5e-6, momentum=0.9, weight_decay=5e-4):
+        """Accumulate + clamp + SGD on the current step's gradient buffer (after an all-reduce of ``train_grads_tensor``)."""
+        check(lib.ivosw_assess_train_apply(self._h, lr, momentum, weight_decay, _stream(self.device)))
+
+    def train_export(self, want_grads=False):
+        """State dict (reference key names) of the parameters and BatchNorm buffers after the steps so far
+        [, accumulated clamped gradients keyed like the parameters]."""
+        n = int(lib.ivosw_assess_blob_floats())
+        blob = np.empty(n, dtype=np.float32)
+        grad = np.empty(n, dtype=np.float32) if want_grads else None
+        check(lib.ivosw_assess_train_export(self._h, _np_ptr(blob), _np_ptr(grad), _stream(self.device)))
+        sd = unpack_assess(blob, self._train_template)
+        return (sd, unpack_assess(grad, self._train_template, grads=True)) if want_grads else sd
+
+    def train_grads(self):
+        """The current step's raw gradient as a flat CUDA tensor view (blob order) — what a data-parallel run all-reduces."""
+        p = C.c_void_p()
+        n = C.c_size_t(0)
+        check(lib.ivosw_assess_train_grads(self._h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    # ------------------------------------------------------------------ peer-memory gather (csrc/gather.cu)
+    def gather_create(self, world, rank, capacity=1024):
+        """Allocates this rank's gather buffer; returns its 64-byte IPC handle (bytes) for the start-up exchange."""
+        h = (C.c_ubyte * 64)()
+        check(lib.ivosw_gather_create(self._h, world, rank, capacity, h))
+        self._gather = {"world": world, "rank": rank, "capacity": capacity, "open": False}
+        return bytes(h)
+
+    def gather_open(self, handles):
+        """handles: world x 64 bytes in rank order."""
+        assert len(handles) == 64 * self._gather["world"]
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        check(lib.ivosw_gather_open(self._h, buf))
+        self._gather["open"] = True
+
+    @property
+    def gather_ready(self):
+        g = getattr(self, "_gather", None)
+        return bool(g and g["open"])
+
+    def gather_post(self, mq_local, offset):
+        """Posts this rank's slice (CUDA float64 tensor, may be empty) of the current round into every rank's buffer."""
+        n = 0 if mq_local is None else mq_local.numel()
+        check(lib.ivosw_gather_post(self._h, _ptr(mq_local) if n else None, n, offset, _stream(self.device)))
+
+    def agent_action_gathered(self, annotated_counts, want_quality=True):
+        """Waits for every rank's slice of the round, then Brain + argmax: (next_frame, q[T], mask_quality[T] or None)."""
+        ann = np.ascontiguousarray(annotated_counts, dtype=np.float64)
+        T = ann.shape[0]
+        q = np.empty(T, dtype=np.float32)
+        mq = np.empty(T, dtype=np.float64) if want_quality else None
+        nf = C.c_int(-1)
+        check(lib.ivosw_agent_action_gathered(self._h, _np_ptr(ann), T, _np_ptr(q), C.byref(nf), _np_ptr(mq),
+                                              _stream(self.device)))
+        return int(nf.value), q, mq
 
     def stage_timing(self, on=True):
         check(lib.ivosw_stage_timing(self._h, 1 if on else 0))

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir, T, H, W, O):
+def _worker(rank, world, port, out_dir, T, H, W, O, peer):
     for p in (REPO, os.path.join(REPO, "ivos-w_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -25,6 +25,8 @@ def _worker(rank, world, port, out_dir, T, H, W, O):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     eng = Engine(rank)
+    os.environ["IVOSW_PEER_GATHER"] = "1" if peer else "0"
+    assert ivdist.setup_peer_gather(eng) == bool(peer)         # peer: csrc/gather.cu over cudaIpc-mapped NVLink memory
     eng.load_assess(synth.assess_state_dict(0))
     eng.load_brain(synth.brain_state_dict(0))
     all_F, all_P, annotated = synth.make_clip(21, T, H, W, O, "atnet")
@@ -49,11 +51,12 @@ def _worker(rank, world, port, out_dir, T, H, W, O):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("T", [16, 13])
-def test_sharded_round_matches_single_gpu(tmp_path, T):
+@pytest.mark.parametrize("T,peer", [(16, 1), (13, 1), (16, 0), (1, 1)])
+def test_sharded_round_matches_single_gpu(tmp_path, T, peer):
+    """T = 13: ragged shards; T = 1: the second rank's shard is empty (it still has to post its flag)."""
     world = 2
-    port = 29700 + (os.getpid() + T) % 200
-    mp.spawn(_worker, args=(world, port, str(tmp_path), T, 240, 432, 2), nprocs=world, join=True)
+    port = 29700 + (os.getpid() + 7 * T + peer) % 200
+    mp.spawn(_worker, args=(world, port, str(tmp_path), T, 240, 432, 2, peer), nprocs=world, join=True)
     full = np.load(tmp_path / "full.npz")
     for r in range(world):
         d = np.load(tmp_path / ("r%d.npz" % r))

@@ -309,3 +309,39 @@ def test_stack_kernel_matches_per_layer_kernels():
     e.close()
     assert float(np.abs(fused["scores"] - res[0]["scores"]).max()) < 2e-5
     assert fused["next_frame"] == res[0]["next_frame"]
+
+
+def test_wide_dynamic_range_and_saturation_counter():
+    """Activations far from O(1): the split-fp16 planes carry x = hi + lo/2048 with fp16's exponent range.  Trunks scaled
+    by 300x and by 1/300 (the stem's BatchNorm) must still agree with the fp32 oracle; a trunk scaled until it leaves the
+    fp16 range must be REPORTED (ivosw_conv_saturation_count), not silently clamped."""
+    from ivosw.engine import Engine
+    from oracle import round_ref
+    T, H, W, O = 4, 160, 256, 1
+    all_F, all_P, annotated = synth.make_clip(51, T, H, W, O)
+    ann = synth.annotated_counts(annotated, T)
+    F_d, P_d = torch.from_numpy(all_F).cuda(), torch.from_numpy(all_P).cuda()
+    brain_sd = synth.brain_state_dict(0)
+    e = Engine(0, CONV_MODE)
+    e.load_brain(brain_sd)
+    for gain in (300.0, 1.0 / 300.0):
+        sd = {k: v.clone() for k, v in synth.assess_state_dict(0).items()}
+        sd["Encoder.bn1.weight"] *= gain
+        sd["Encoder.bn1.bias"] *= gain
+        sd["fc1.weight"] /= max(gain, 1.0)                    # keep the scores O(1) for the large trunk
+        e.load_assess(sd)
+        r = e.round_device(F_d, P_d, ann, want_scores=True)
+        ref = round_ref.recommend_frame_wild_ours(sd, brain_sd, all_F, all_P, annotated)
+        scale = max(1.0, float(np.abs(ref["scores"]).max()))
+        assert float(np.abs(r["scores"] - ref["scores"]).max()) <= 1e-4 * scale, (gain, r["scores"], ref["scores"])
+        assert e.saturation_count() == 0
+    sd = {k: v.clone() for k, v in synth.assess_state_dict(0).items()}
+    sd["Encoder.bn1.weight"] *= 3e4
+    sd["Encoder.bn1.bias"] *= 3e4
+    e.load_assess(sd)
+    e.round_device(F_d, P_d, ann, want_scores=True)
+    assert e.saturation_count() > 0                           # loud: the caller can see that the range guard fired
+    from ivosw._lib import lib
+    assert b"fp16 range" in lib.ivosw_last_error()
+    assert e.saturation_count() == 0                          # the read above reset the counter
+    e.close()

@@ -1,0 +1,82 @@
+"""GPU (-m gpu): the AssessNet optimisation step (csrc/train.cu, BASELINE config C5) against the fixture produced by the
+reference's own AssessNet in train mode + torch.optim.SGD (tests/golden/assess_train.npz: two consecutive iterations of
+quality_assessment.py::train's loop body, no zero_grad between them).
+
+Tolerances: predictions / loss 1e-4 (fp32 forward through 54 train-mode BatchNorms at batch 4); gradients 3e-2 of a
+tensor's largest entry — the band tests/test_oracle_golden.py measured for ANY fp32-grade re-implementation whose ROI crop
+differs from ATen's by ~5e-6 (53 batch-statistics layers at batch 4 amplify it); parameters after the steps 1e-7 (the
+update is lr = 5e-6 times a clamped gradient); BatchNorm running statistics 1e-4."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mg(golden_dir):
+    sys.path.insert(0, golden_dir)
+    try:
+        import make_golden as mg
+    finally:
+        sys.path.pop(0)
+    return mg
+
+
+def test_train_step_vs_reference_golden(golden_dir):
+    from ivosw.engine import Engine
+    mg = _mg(golden_dir)
+    g = np.load(os.path.join(golden_dir, "assess_train.npz"))
+    e = Engine(0)
+    sd0 = mg.train_state_dict()
+    e.train_begin(sd0)
+    for step in range(2):
+        imgs, probs, targets, valid = mg.synth_train_batch(step)
+        loss, pred = e.train_step(torch.from_numpy(imgs).cuda(), torch.from_numpy(probs).cuda(), targets, valid, **mg.TRAIN_HP)
+        np.testing.assert_allclose(pred, g["pred%d" % step], rtol=1e-4, atol=1e-4)
+        assert abs(loss - float(g["loss%d" % step])) <= 1e-4 * abs(float(g["loss%d" % step]))
+        sd, grads = e.train_export(want_grads=True)
+        for k in mg.TRAIN_KEYS:
+            stride = 101 if sd[k].numel() > 10000 else 1
+            ref = g["grad%d_%s" % (step, k)]
+            np.testing.assert_allclose(grads[k].numpy().reshape(-1)[::stride], ref, rtol=0,
+                                       atol=3e-2 * float(np.abs(ref).max()) + 1e-12, err_msg="grad %d %s" % (step, k))
+            np.testing.assert_allclose(sd[k].numpy().reshape(-1)[::stride], g["param%d_%s" % (step, k)], rtol=0, atol=1e-7,
+                                       err_msg="param %d %s" % (step, k))
+    for k in mg.TRAIN_BUFFERS:
+        if k.endswith("num_batches_tracked"):
+            continue                                  # a host-side counter in the reference; the blob does not carry it
+        np.testing.assert_allclose(sd[k].numpy().reshape(-1).astype(np.float64), g["buf_" + k].astype(np.float64), rtol=1e-4,
+                                   atol=1e-5, err_msg=k)
+    # the exported state loads straight back into the inference path
+    e.load_assess(sd)
+    imgs, probs, _, _ = mg.synth_train_batch(0)
+    s = e.assess_forward(torch.from_numpy(imgs).cuda(), torch.from_numpy(probs).cuda())
+    assert torch.isfinite(s).all()
+    e.close()
+
+
+def test_train_step_no_valid_sample_and_determinism(golden_dir):
+    """`if counter == 0: continue` (:259): no backward, no update.  Two engines stepping on the same data agree bit for bit
+    (fixed-order reductions, no atomics)."""
+    from ivosw.engine import Engine
+    mg = _mg(golden_dir)
+    imgs, probs, targets, valid = mg.synth_train_batch(0)
+    F, P = torch.from_numpy(imgs).cuda(), torch.from_numpy(probs).cuda()
+    outs = []
+    for _ in range(2):
+        e = Engine(0)
+        e.train_begin(mg.train_state_dict())
+        loss0, _ = e.train_step(F, P, targets, np.zeros(len(valid), bool), **mg.TRAIN_HP)
+        assert loss0 is None
+        sd_a = e.train_export()
+        np.testing.assert_array_equal(sd_a["fc1.weight"].numpy(), mg.train_state_dict()["fc1.weight"].numpy())
+        loss, pred = e.train_step(F, P, targets, valid, **mg.TRAIN_HP)
+        sd, grads = e.train_export(want_grads=True)
+        outs.append((loss, pred, sd["Encoder.res3.1.conv2.weight"].numpy(), grads["Encoder.conv1.weight"].numpy()))
+        e.close()
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        np.testing.assert_array_equal(a, b)

@@ -51,6 +51,30 @@ def test_sass_is_sm100a(built_lib):
     assert "sm_100a" in out
 
 
+def test_sass_is_blackwell_native(built_lib):
+    """The encoder kernels really are tcgen05 / TMEM / TMA code (B200_PROFILING.md: the PTX names never appear in SASS:
+    tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, TMA -> UTMALDG / UTMASTG / UBLKCP), with no legacy mma.sync (HMMA)."""
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    per_fn, fn = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            per_fn[fn] = set()
+        elif fn:
+            for op in ("UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "HMMA.", "HGMMA"):
+                if op in line:
+                    per_fn[fn].add(op)
+    conv = [f for f in per_fn if "conv_tc_kernel" in f or "conv_stack_kernel" in f]
+    assert len(conv) >= 6
+    for f in conv:
+        assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= per_fn[f], (f, per_fn[f])
+    staged = [f for f in conv if "Lb1E" in f or "conv_stack" in f]
+    assert staged and all("UTMASTG" in per_fn[f] for f in staged)
+    stem = [f for f in per_fn if "stem_tc_kernel" in f]
+    assert stem and {"UTCHMMA", "UBLKCP", "LDTM"} <= per_fn[stem[0]]
+    assert not any({"HMMA.", "HGMMA"} & ops for ops in per_fn.values())
+
+
 def test_blob_sizes(built_lib):
     from ivosw import _lib, engine
     assert arch.BRAIN_NUM_PARAMS == _lib.BRAIN_NUM_PARAMS == 180993
