@@ -25,6 +25,10 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: if the environment asks NCCL for a banner (NCCL_DEBUG=VERSION/WARN/INFO print
+# "NCCL version ..." on stdout by default), send NCCL's own log to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(REPO, "ivos-w_b200")
 for p in (REPO, PKG):
@@ -293,6 +297,10 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # clocks / throttle reasons: nvidia-smi needs a few hundred ms before its first sample, so it starts streaming now
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     eng = Engine(local_rank, args.conv_mode)
     peer_gather = ivdist.setup_peer_gather(eng) if world > 1 else False
     assess_sd, brain_sd = synth.assess_state_dict(0), synth.brain_state_dict(0)
@@ -336,9 +344,6 @@ def run_ours(args):
         return float(ms.item())
 
     # ---- warm-up, then the timed region with clocks sampled under load
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     # Per-stage CUDA-event timing (the roofline leg).  N == 1: recorded live inside the timed region (the
     # library syncs once per round, so the events of every CUDA-graph replay are read back).  N > 1: the
     # shard path is fully asynchronous, so the timed region runs untimed graphs and the stage times come

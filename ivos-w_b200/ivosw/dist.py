@@ -127,3 +127,25 @@ def dqn_update_data_parallel(engine, state, new_state, action, reward_step, rewa
         loss = float(lt.item()) / world
     engine.dqn_apply(grads, lr=lr, weight_decay=weight_decay)
     return loss
+
+
+def assess_train_step_data_parallel(engine, imgs, probs, targets, valid, lr=5e-6, momentum=0.9, weight_decay=5e-4, group=None):
+    """BASELINE config C5, data-parallel: every rank runs forward + backward of quality_assessment.py::train's loop body
+    on ITS samples (csrc/train.cu, apply_update = 0), the raw gradients (23.5 M fp32 = 94 MB, blob order) are averaged with
+    ONE NCCL all-reduce in place in the library's buffer, then every rank applies the identical accumulate + clamp + SGD
+    update.  BatchNorm statistics are per rank (the reference is single-GPU: SURVEY.md §8(f) flags the difference).
+    Returns the mean loss over ranks (None when no rank had a valid sample)."""
+    loss, _ = engine.train_step(imgs, probs, targets, valid, lr=lr, momentum=momentum, weight_decay=weight_decay, apply=False)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    g = engine.train_grads_tensor()
+    stat = torch.tensor([0.0 if loss is None else loss, 0.0 if loss is None else 1.0], device=engine.device, dtype=torch.float64)
+    if world > 1:
+        if loss is None:
+            g.zero_()                       # a rank that skipped backward contributes nothing
+        dist.all_reduce(g, group=group)
+        dist.all_reduce(stat, group=group)
+        g /= world
+    if float(stat[1]) == 0.0:
+        return None
+    engine.train_apply(lr=lr, momentum=momentum, weight_decay=weight_decay)
+    return float(stat[0] / stat[1])

@@ -379,12 +379,16 @@ class Engine:
         sd = unpack_assess(blob, self._train_template)
         return (sd, unpack_assess(grad, self._train_template, grads=True)) if want_grads else sd
 
-    def train_grads(self):
-        """The current step's raw gradient as a flat CUDA tensor view (blob order) — what a data-parallel run all-reduces."""
+    def train_grads_tensor(self):
+        """The current step's raw gradient (blob order) as a flat CUDA tensor that ALIASES the library's buffer (no copy):
+        what a data-parallel run all-reduces in place between train_step(apply=False) and train_apply()."""
         p = C.c_void_p()
         n = C.c_size_t(0)
         check(lib.ivosw_assess_train_grads(self._h, C.byref(p), C.byref(n)))
-        return p.value, int(n.value)
+
+        class _View:            # CUDA array interface: torch wraps the pointer without copying
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<f4", "data": (int(p.value), False), "version": 2}
+        return torch.as_tensor(_View(), device=self.device)
 
     # ------------------------------------------------------------------ peer-memory gather (csrc/gather.cu)
     def gather_create(self, world, rank, capacity=1024):

@@ -80,3 +80,24 @@ def test_train_step_no_valid_sample_and_determinism(golden_dir):
     assert outs[0][0] == outs[1][0]
     for a, b in zip(outs[0][1:], outs[1][1:]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_train_step_split_then_apply_equals_fused(golden_dir):
+    """The data-parallel form on one rank: train_step(apply=False) + the aliased gradient tensor + train_apply gives the
+    same parameters as the fused step (ivosw.dist.assess_train_step_data_parallel without a process group)."""
+    from ivosw import dist as ivdist
+    from ivosw.engine import Engine
+    mg = _mg(golden_dir)
+    imgs, probs, targets, valid = mg.synth_train_batch(0)
+    F, P = torch.from_numpy(imgs).cuda(), torch.from_numpy(probs).cuda()
+    a, b = Engine(0), Engine(0)
+    a.train_begin(mg.train_state_dict()); b.train_begin(mg.train_state_dict())
+    la, _ = a.train_step(F, P, targets, valid, **mg.TRAIN_HP)
+    lb = ivdist.assess_train_step_data_parallel(b, F, P, targets, valid, **mg.TRAIN_HP)
+    assert la == lb
+    g = b.train_grads_tensor()
+    assert g.is_cuda and g.numel() == 23566343 and float(g.abs().max()) > 0
+    sa, sb = a.train_export(), b.train_export()
+    for k in ("fc1.weight", "Encoder.conv1.weight", "Encoder.res4.3.conv3.weight", "Encoder.res2.0.bn1.bias"):
+        np.testing.assert_array_equal(sa[k].numpy(), sb[k].numpy())
+    a.close(); b.close()
