@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
         // rewritten, the previous pass must have been read out
         uint32_t passes[2] = {0, 0};            // passes handed to each store lane so far
         int prev_owner = -1, t_cta = 0;
-        uint32_t sat = 0;
+        __half2 sat = __float2half2_rn(0.f);            // running max of |hi| (fp16 range guard)
         const uint32_t stg_hi = smem_u32(smem + CS_STG_OFF), stg_lo = stg_hi + TC_BM * 128;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
             int tiles_n;
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
                         const __half2 h = __floats2half2_rn(a, b);
                         const float2 hf = __half22float2(h);
                         oh[u] = *reinterpret_cast<const uint32_t*>(&h);
-                        sat |= sat_probe(oh[u]);
+                        sat = __hmax2(sat, __habs2(*reinterpret_cast<const __half2*>(&oh[u])));
                         ol[u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                     }
                     const int owner = t_cta & (CS_STORE_WARPS - 1);
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
                 atomicAdd(P.prof + 704 + T.layer, (unsigned long long)e_fence);
             }
         }
-        if (sat & 0x80008000u) atomicAdd(P.sat_count, 1ull);
+        if (sat_hit(sat)) atomicAdd(P.sat_count, 1ull);
     } else if (lane == 0) {
         // ====================================== store lanes ======================================
         // Two store warps (one lane each): the first sends the even tiles of this CTA, the second the odd ones.  A tile may only be published once its writes have

@@ -263,22 +263,49 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             uint32_t soff[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) soff[q] = (uint32_t)row * 128u + (uint32_t)(((2 * csub + q) ^ (row & 7)) << 4);
-            // ReLU and the fp16 range guard as ONE clamp: [0, 65504] or [-65504, 65504]
-            const float lo_clamp = relu ? 0.f : -65504.f;
+            // (The residual tile is copied into registers as soon as it lands and its ring slot handed straight back.  A
+            //  variant that left it in the slot and read it pass by pass — no 32 extra registers, no spills, the form
+            //  conv_stack.cu uses — was measured here too: equal in the bench, but slower per layer under ncu
+            //  (res2 conv3 268 vs 189 us): with 2-3 ring slots a residual block that stays until the tile's last pass keeps
+            //  the next tile's residual from being fetched during this tile's epilogue.)
+            float rf[NP][16];                                   // this thread's residual values: [pass][column]
+#pragma unroll
+            for (int g = 0; g < NP; ++g)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) rf[g][k] = 0.f;
             int stage = 0, t_local = 0;                         // ring position of the residual blocks
-            uint32_t sat = 0;
+            __half2 sat = __float2half2_rn(0.f);            // running max of |hi| (fp16 range guard)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
-                // The residual tile stays in its ring slot and is read pass by pass, right where it is added.  (Copying all
-                // of it into registers at the start of the tile freed the slot a little earlier but cost 32 registers per
-                // thread: the epilogue spilled to local memory, and beside 227 KB of shared memory the L1 is too small to
-                // hold the spills and the BatchNorm vectors — measured in conv_stack.cu's per-phase profile: the arithmetic
-                // phase of a pass took 2 175 cycles, 870 without the spills.)
-                uint32_t rs = 0;
                 if (has_res) {
+                    // residual tile -> registers (every epilogue thread waits on every use of res_full, in order),
+                    // then the slot goes straight back to the producer
                     stage = (stage + num_kb) % S::STAGES;
                     mbar_wait(&res_full[t_local & 1], (uint32_t)(t_local >> 1) & 1u);
-                    rs = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint32_t rs = smem_u32(smem + stage * S::STAGE_BYTES);
+#pragma unroll
+                    for (int g = 0; g < NP; ++g)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint4 h4 = lds128(rs + g * 2 * TC_BM * 128 + soff[q]);
+                            const uint4 l4 = x3 ? lds128(rs + g * 2 * TC_BM * 128 + TC_BM * 128 + soff[q]) : make_uint4(0, 0, 0, 0);
+                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
+                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
+                                rf[g][q * 8 + u * 2 + 0] = fmaf(lf.x, 1.0f / 2048.0f, hf.x);
+                                rf[g][q * 8 + u * 2 + 1] = fmaf(lf.y, 1.0f / 2048.0f, hf.y);
+                            }
+                        }
+                    // The slot is about to be overwritten by TMA (async proxy): the generic-proxy reads above must be
+                    // complete first.  A barrier alone orders them against other threads' generic accesses only —
+                    // releasing right after it let the next block land under still-queued reads.
+                    fence_proxy_async();
+                    group_bar(3, 512);
+                    if (leader) mbar_arrive(&empty_bar[stage]);
+                    stage = (stage + 1) % S::STAGES;
+                    ++t_local;
                 }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
@@ -286,12 +313,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                    if (has_res) {
-                        group_bar(3, 512);
-                        if (leader) mbar_arrive(&empty_bar[stage]);
-                        stage = (stage + 1) % S::STAGES;
-                        ++t_local;
-                    }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     continue;
                 }
@@ -303,53 +324,45 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     uint32_t r0[16], r1[16];
                     tmem_ld16(t_d0, r0);
                     if (x3) tmem_ld16(t_d0 + BN, r1);
-                    // BatchNorm vectors of this thread's 16 channels: issued before the TMEM wait, their latency hides behind it
-                    float sc[16], sh[16];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.scale + n + q * 4));
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.shift + n + q * 4));
-                        sc[q * 4] = a4.x; sc[q * 4 + 1] = a4.y; sc[q * 4 + 2] = a4.z; sc[q * 4 + 3] = a4.w;
-                        sh[q * 4] = b4.x; sh[q * 4 + 1] = b4.y; sh[q * 4 + 2] = b4.z; sh[q * 4 + 3] = b4.w;
-                    }
                     tmem_ld_wait();
                     if (g == NP - 1) {                          // last TMEM read of the tile: hand the accumulator back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                     }
-                    float v[16];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        float a = __uint_as_float(r0[k]);
-                        if (x3) a = fmaf(__uint_as_float(r1[k]), 1.0f / 2048.0f, a);
-                        v[k] = fmaf(a, sc[k], sh[k]);
-                    }
-                    if (has_res) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const uint4 h4 = lds128(rs + g * 2 * TC_BM * 128 + soff[q]);
-                            const uint4 l4 = x3 ? lds128(rs + g * 2 * TC_BM * 128 + TC_BM * 128 + soff[q]) : make_uint4(0, 0, 0, 0);
-                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
-                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
-                                v[q * 8 + u * 2 + 0] += fmaf(lf.x, 1.0f / 2048.0f, hf.x);
-                                v[q * 8 + u * 2 + 1] += fmaf(lf.y, 1.0f / 2048.0f, hf.y);
-                            }
-                        }
-                    }
                     uint32_t oh[8], ol[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float a = fminf(fmaxf(v[u * 2], lo_clamp), 65504.f);
-                        const float b = fminf(fmaxf(v[u * 2 + 1], lo_clamp), 65504.f);
-                        const __half2 h = __floats2half2_rn(a, b);
-                        const float2 hf = __half22float2(h);
-                        oh[u] = *reinterpret_cast<const uint32_t*>(&h);
-                        sat |= sat_probe(oh[u]);
-                        ol[u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.scale + n + q * 8));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.scale + n + q * 8 + 4));
+                        const float4 h0 = __ldg(reinterpret_cast<const float4*>(P.shift + n + q * 8));
+                        const float4 h1 = __ldg(reinterpret_cast<const float4*>(P.shift + n + q * 8 + 4));
+                        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                        float v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            float a = __uint_as_float(r0[q * 8 + k]);
+                            if (x3) a = fmaf(__uint_as_float(r1[q * 8 + k]), 1.0f / 2048.0f, a);
+                            v[k] = fmaf(a, sc[k], sh[k]);
+                        }
+                        if (has_res) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] += rf[g][q * 8 + k];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float a = v[u * 2], b = v[u * 2 + 1];
+                            if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            else { a = fmaxf(a, -65504.f); b = fmaxf(b, -65504.f); }
+                            a = fminf(a, 65504.f);                                      // fp16 range guard
+                            b = fminf(b, 65504.f);
+                            const __half2 h = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h);
+                            oh[q * 4 + u] = *reinterpret_cast<const uint32_t*>(&h);
+                            sat = __hmax2(sat, __habs2(*reinterpret_cast<const __half2*>(&oh[q * 4 + u])));
+                            ol[q * 4 + u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                        }
                     }
                     uint8_t* stg = smem + S::STG_OFF + (S::NSTG == 2 ? g * 2 * TC_BM * 128 : 0);
                     const uint32_t stg_hi = smem_u32(stg), stg_lo = stg_hi + TC_BM * 128;
@@ -362,24 +375,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         sts128(stg_hi + soff[q], make_uint4(oh[q * 4], oh[q * 4 + 1], oh[q * 4 + 2], oh[q * 4 + 3]));
                         sts128(stg_lo + soff[q], make_uint4(ol[q * 4], ol[q * 4 + 1], ol[q * 4 + 2], ol[q * 4 + 3]));
                     }
-                    // generic-proxy smem writes -> visible to the TMA store; on the last pass the fence also covers this
-                    // thread's reads of the residual block, whose slot returns to the TMA producer after the barrier
-                    fence_proxy_async();
+                    fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA store
                     group_bar(1, 512);                      // half tile staged
                     if (leader) {
-                        if (has_res && g == NP - 1) mbar_arrive(&empty_bar[stage]);
                         tma_store_2d(&maps.o_hi, stg, nt * BN + g * 64, mt * TC_BM);
                         tma_store_2d(&maps.o_lo, stg + TC_BM * 128, nt * BN + g * 64, mt * TC_BM);
                         bulk_commit();
                     }
                 }
-                if (has_res) { stage = (stage + 1) % S::STAGES; ++t_local; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (leader) bulk_wait0();
-            if (sat & 0x80008000u) atomicAdd(P.sat_count, 1ull);
+            if (sat_hit(sat)) atomicAdd(P.sat_count, 1ull);
         } else {
-            uint32_t sat = 0;
+            __half2 sat = __float2half2_rn(0.f);            // running max of |hi| (fp16 range guard)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const long long m = (long long)mt * TC_BM + row;
@@ -430,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             const __half2 h = __floats2half2_rn(a, b);
                             const float2 hf = __half22float2(h);
                             oh[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                            sat |= sat_probe(oh[j >> 1]);
+                            sat = __hmax2(sat, __habs2(*reinterpret_cast<const __half2*>(&oh[j >> 1])));
                             ol[j >> 1] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                         }
                         uint4* ph = reinterpret_cast<uint4*>(P.out_hi + off);
@@ -448,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (sat & 0x80008000u) atomicAdd(P.sat_count, 1ull);
+            if (sat_hit(sat)) atomicAdd(P.sat_count, 1ull);
         }
     }
     tc_fence_before();

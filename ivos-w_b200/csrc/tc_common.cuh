@@ -132,6 +132,12 @@ __device__ __forceinline__ bool elect_one() {
 // bit 15 of a half lane is set iff that lane holds +-65504 (0x7BFF): the value the range guard clamps to.
 // (0x7BFF + 0x0401 = 0x8000, no carry between the lanes.)  OR-ed over a tile and tested once.
 __device__ __forceinline__ uint32_t sat_probe(uint32_t h2bits) { return (h2bits & 0x7FFF7FFFu) + 0x04010401u; }
+// The epilogues keep a running packed max of |hi| (one HMNMX2 per value pair) and test it once per tile walk:
+// a lane that reached 65504 (or inf) means the range guard clamped something.
+__device__ __forceinline__ bool sat_hit(__half2 m) {
+    const uint32_t b = *reinterpret_cast<const uint32_t*>(&m);
+    return (sat_probe(b) & 0x80008000u) != 0;
+}
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
