@@ -235,6 +235,18 @@ IVOSW_API int ivosw_manet_tail(ivosw_ctx* ctx, const float* logits_dev, int T, i
 IVOSW_API int ivosw_rough_roi(ivosw_ctx* ctx, const float* labels_dev, float* out_dev, int B, int h, int w,
                     int dist, void* stream);
 
+/* ---- MANet feature extractor (IntVOS.extract_feature, call site eval_agent_manet.py:316-328) --------------------
+ * DeepLabv3+ ResNet-101 (output stride 16) + ASPP + shortcut decoder + semantic-embedding head: frames B x 3 x H x W
+ * (normalised, device) -> embedding B x 100 x h/4 x w/4 fp32 (device), e.g. 480 x 854 -> 120 x 214.
+ * RESTATEMENT: the network's source is not part of the reference tree; the architecture and the parameter blob follow
+ * ivosw/manet_arch.py (hyper-parameters of utils/config_manet/config.py:108-120) and parity is claimed against
+ * oracle/manet_encoder_ref.py only (parity unpinned).  Blob: per convolution in manet_arch.convs()
+ * order, weight as OHWI then BatchNorm gamma, beta, running_mean (minus the conv bias where there is one), running_var. */
+IVOSW_API size_t ivosw_manet_encoder_blob_floats(void);
+IVOSW_API int ivosw_manet_encoder_load(ivosw_ctx* ctx, const float* blob_host, size_t n_floats);
+IVOSW_API int ivosw_manet_encoder_forward(ivosw_ctx* ctx, const float* frames_dev, int B, int H, int W, float* embedding_dev,
+                                          void* stream);
+
 /* ---- AssessNet optimisation step (quality_assessment.py::train :240-269; BASELINE config C5) ---------------------
  * ivosw_assess_train_begin   (re)starts training from a parameter blob in ivosw_assess_load's layout: parameters and
  *                            BatchNorm buffers go to the device, gradients and SGD momentum buffers start at zero.

@@ -469,6 +469,7 @@ void ivosw_destroy(ivosw_ctx* c) {
     conv_stack_release(c);
     gather_release(c);
     train_release(c);
+    manet_encoder_release(c);
     release(c->stack_arena);
     if (c->stem_w) cudaFree(c->stem_w);
     if (c->stem_scale) cudaFree(c->stem_scale);
@@ -1176,6 +1177,32 @@ int ivosw_dqn_set_optimizer(ivosw_ctx* c, const float* m_dev, const float* v_dev
     IVOSW_CUDA(cudaMemcpyAsync(c->adam_m, m_dev, nb, cudaMemcpyDeviceToDevice, s));
     IVOSW_CUDA(cudaMemcpyAsync(c->adam_v, v_dev, nb, cudaMemcpyDeviceToDevice, s));
     c->adam_step = step;
+    return IVOSW_OK;
+}
+
+// ---------------------------------------------------------------- MANet feature extractor (restatement, parity unpinned)
+size_t ivosw_manet_encoder_blob_floats(void) { return manet_encoder_blob_floats(); }
+
+int ivosw_manet_encoder_load(ivosw_ctx* c, const float* blob, size_t n_floats) {
+    IVOSW_REQUIRE(c && blob, "null pointer");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    return manet_encoder_load(c, blob, n_floats);
+}
+
+int ivosw_manet_encoder_forward(ivosw_ctx* c, const float* frames_dev, int B, int H, int W, float* embedding_dev, void* stream) {
+    IVOSW_REQUIRE(c && frames_dev && embedding_dev, "null pointer");
+    IVOSW_REQUIRE(B >= 1 && H >= 16 && W >= 16, "B, H, W");
+    IVOSW_REQUIRE(c->conv_mode != IVOSW_CONV_SIMT_FP32, "the encoder runs on the tensor-core modes only");
+    IVOSW_CUDA(cudaSetDevice(c->device));
+    const int terms = c->conv_mode == IVOSW_CONV_TC_FP16X3 ? 3 : 1;
+    const int chunk = 8;                        // frames per pass (workspace ~ 0.35 GB per 480 x 854 frame)
+    const int h4 = (((H + 6 - 7) / 2 + 1) + 2 - 3) / 2 + 1, w4 = (((W + 6 - 7) / 2 + 1) + 2 - 3) / 2 + 1;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        int rc = manet_encoder_forward(c, frames_dev + (size_t)b0 * 3 * H * W, nb, H, W, embedding_dev + (size_t)b0 * 100 * h4 * w4,
+                                       terms, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     return IVOSW_OK;
 }
 

@@ -35,7 +35,11 @@ struct TcParams {
     int num_taps, cin_blocks;     // K blocks = num_taps * cin_blocks ...
     int num_kb;                   // ... unless two GEMMs share the accumulator (kb_split > 0): blocks [0, kb_split) read
     int kb_split;                 //     the first activation tensor (tap 0), blocks [kb_split, num_kb) the second (tap 1)
-    int out_hw;                   // OH == OW
+    int out_hw;                   // output canvas height (AssessNet: OH == OW, the whole canvas is valid)
+    int out_wp;                   // output canvas width (a power of two; > 128: a tile is part of one row)
+    int valid_h, valid_w;         // the encoder of the VOS backbone works on canvases larger than the feature map
+                                  // (30 x 54 on 32 x 64 ...): positions outside valid_h x valid_w are written as zeros,
+                                  // so that they act as the zero padding of the next convolution (0 = no masking)
     int tiles_m, tiles_n;
     int relu, terms;              // terms: 3 (split-fp16) or 1
     int dbg;                      // measurement only (IVOSW_TC_DEBUG): 1 = no TMA operand loads, 2 = no MMAs, 4 = no staged epilogue work
@@ -131,13 +135,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = x3 ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
-            const int pix_per_img = P.out_hw * P.out_hw;
+            const int pix_per_img = P.out_hw * P.out_wp;
             int t_local = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
                 const int m0 = mt * TC_BM;
                 const int n_img = m0 / pix_per_img;
-                const int h0 = (m0 - n_img * pix_per_img) / P.out_hw;
+                const int rem0 = m0 - n_img * pix_per_img;
+                const int h0 = rem0 / P.out_wp, w0 = rem0 - h0 * P.out_wp;     // w0 != 0 only on canvases wider than a tile
                 for (int kb = 0; kb < num_kb; ++kb) {
                     int tap, cb;
                     const CUtensorMap* mh = &maps.a_hi;
@@ -156,10 +161,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     }
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     const int c0 = tp.c_add + cb * TC_BK;
-                    tma_load_5d(st, mh, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                    tma_load_5d(st, mh, &full_bar[stage], c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
                     tma_load_2d(st + 2 * S::A_BYTES, &maps.w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
                     if (x3) {
-                        tma_load_5d(st + S::A_BYTES, ml, &full_bar[stage], c0, tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                        tma_load_5d(st + S::A_BYTES, ml, &full_bar[stage], c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
                         tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
                     }
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
@@ -275,8 +280,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 for (int k = 0; k < 16; ++k) rf[g][k] = 0.f;
             int stage = 0, t_local = 0;                         // ring position of the residual blocks
             __half2 sat = __float2half2_rn(0.f);            // running max of |hi| (fp16 range guard)
+            const bool masking = P.valid_w > 0;                 // kernel-uniform: canvases larger than the feature map
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
+                bool row_valid = true;
+                if (masking) {                                  // this thread's output pixel inside the feature map?
+                    const int rem = (mt * TC_BM + row) % (P.out_hw * P.out_wp);
+                    row_valid = (rem / P.out_wp) < P.valid_h && (rem % P.out_wp) < P.valid_w;
+                }
                 if (has_res) {
                     // residual tile -> registers (every epilogue thread waits on every use of res_full, in order),
                     // then the slot goes straight back to the producer
@@ -363,6 +374,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             sat = __hmax2(sat, __habs2(*reinterpret_cast<const __half2*>(&oh[q * 4 + u])));
                             ol[q * 4 + u] = pack_half2((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
                         }
+                    }
+                    if (masking && !row_valid) {            // outside the feature map: zeros = the next layer's padding
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { oh[u] = 0u; ol[u] = 0u; }
                     }
                     uint8_t* stg = smem + S::STG_OFF + (S::NSTG == 2 ? g * 2 * TC_BM * 128 : 0);
                     const uint32_t stg_hi = smem_u32(stg), stg_lo = stg_hi + TC_BM * 128;
@@ -527,6 +542,34 @@ int encode_act_map(CUtensorMap* map, const __half* base, int B, int H, int C, in
     return encode_map(map, base, 5, dims, strides, box);
 }
 
+// The same for rectangular power-of-two canvases (Hp x Wp): a 128-pixel tile is Hb rows of Wb = min(Wp_out, 128) pixels.
+int encode_act_map_g(CUtensorMap* map, const __half* base, int B, int Hp, int Wp, int C, int stride, int out_hp, int out_wp) {
+    const int Wb = out_wp < TC_BM ? out_wp : TC_BM;
+    const int Hb = (TC_BM / Wb) < out_hp ? (TC_BM / Wb) : out_hp;
+    const int Nb = TC_BM / (Wb * Hb);
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)Wb, 1, (cuuint32_t)Hb, (cuuint32_t)Nb};
+    const cuuint64_t e = sizeof(__half);
+    if (stride == 1) {
+        dims[0] = C; dims[1] = Wp; dims[2] = 1; dims[3] = Hp; dims[4] = B > Nb ? B : Nb;
+        strides[0] = (cuuint64_t)C * e; strides[1] = (cuuint64_t)Wp * C * e; strides[2] = (cuuint64_t)Wp * C * e;
+        strides[3] = (cuuint64_t)Hp * Wp * C * e;
+    } else {
+        dims[0] = 2 * C; dims[1] = Wp / 2; dims[2] = 2; dims[3] = Hp / 2; dims[4] = B > Nb ? B : Nb;
+        strides[0] = (cuuint64_t)2 * C * e; strides[1] = (cuuint64_t)Wp * C * e; strides[2] = (cuuint64_t)2 * Wp * C * e;
+        strides[3] = (cuuint64_t)Hp * Wp * C * e;
+    }
+    return encode_map(map, base, 5, dims, strides, box);
+}
+
+// output / residual tile of a tensor whose rows are `ld` channels apart (a channel slice of a concatenation buffer)
+int encode_out_map_ld(CUtensorMap* map, const __half* base, long long M, int Cout, int ld) {
+    cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+    cuuint32_t box[2] = {64, (cuuint32_t)TC_BM};
+    return encode_map(map, base, 2, dims, strides, box);
+}
+
 int encode_w_map(CUtensorMap* map, const __half* base, int K, int Cout, int BN) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(__half)};
@@ -625,7 +668,7 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
     P.Cout = L.cout; P.Cin = L.cin;
     P.num_taps = L.k * L.k; P.cin_blocks = L.cin / TC_BK;
     P.num_kb = K / TC_BK; P.kb_split = fuse ? L.cin / TC_BK : 0;
-    P.out_hw = L.out_hw;
+    P.out_hw = L.out_hw; P.out_wp = L.out_hw;
     P.tiles_m = (P.M + TC_BM - 1) / TC_BM; P.tiles_n = L.cout / BN;
     P.relu = L.relu ? 1 : 0; P.terms = terms;
     { const char* e = getenv("IVOSW_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
@@ -648,6 +691,58 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
         return launch_tc_variant<128, 3, true>(c, maps, P, s);
     }
     return BN == 128 ? launch_tc_variant<128, 3, false>(c, maps, P, s) : launch_tc_variant<64, 4, false>(c, maps, P, s);
+}
+
+// One convolution of the VOS encoder (manet_encoder.cu): rectangular power-of-two canvases around a feature map of any
+// size, dilation, stride 1 or 2, output into a channel slice, optional fused second 1x1 GEMM (the downsample branch)
+// and residual.  Same kernel, staged epilogue, positions outside the feature map written as zeros.
+int launch_conv_tc_g(ivosw_ctx* c, const GConv& L, const SplitAct& in, const SplitAct* in2, const SplitAct* residual,
+                     const SplitAct& out, int out_ld, int B, int terms, cudaStream_t s) {
+    const int BN = L.cout >= 128 ? 128 : 64;
+    const int k3 = L.k * L.k * L.cin;
+    const int K = k3 + L.cin2;
+    int rc;
+    TcMaps maps;
+    memset(&maps, 0, sizeof maps);
+    TcParams P;
+    memset(&P, 0, sizeof P);
+    P.M = B * L.out_hp * L.out_wp;
+    if ((rc = encode_act_map_g(&maps.a_hi, in.hi, B, L.in_hp, L.in_wp, L.cin, L.stride, L.out_hp, L.out_wp))) return rc;
+    if ((rc = encode_act_map_g(&maps.a_lo, in.lo, B, L.in_hp, L.in_wp, L.cin, L.stride, L.out_hp, L.out_wp))) return rc;
+    if (L.cin2) {
+        if ((rc = encode_act_map_g(&maps.a2_hi, in2->hi, B, L.in2_hp, L.in2_wp, L.cin2, L.stride2, L.out_hp, L.out_wp))) return rc;
+        if ((rc = encode_act_map_g(&maps.a2_lo, in2->lo, B, L.in2_hp, L.in2_wp, L.cin2, L.stride2, L.out_hp, L.out_wp))) return rc;
+    }
+    if ((rc = encode_w_map(&maps.w_hi, L.w_hi, K, L.cout, BN))) return rc;
+    if ((rc = encode_w_map(&maps.w_lo, L.w_lo, K, L.cout, BN))) return rc;
+    if ((rc = encode_out_map_ld(&maps.o_hi, out.hi, P.M, L.cout, out_ld))) return rc;
+    if ((rc = encode_out_map_ld(&maps.o_lo, out.lo, P.M, L.cout, out_ld))) return rc;
+    if (residual) {
+        if ((rc = encode_out_map_ld(&maps.r_hi, residual->hi, P.M, L.cout, L.cout))) return rc;
+        if ((rc = encode_out_map_ld(&maps.r_lo, residual->lo, P.M, L.cout, L.cout))) return rc;
+    }
+    P.Cout = L.cout; P.Cin = L.cin;
+    P.num_taps = L.k * L.k; P.cin_blocks = L.cin / TC_BK;
+    P.num_kb = K / TC_BK; P.kb_split = L.cin2 ? k3 / TC_BK : 0;
+    P.out_hw = L.out_hp; P.out_wp = L.out_wp; P.valid_h = L.valid_h; P.valid_w = L.valid_w;
+    P.tiles_m = (P.M + TC_BM - 1) / TC_BM; P.tiles_n = L.cout / BN;
+    P.relu = L.relu; P.terms = terms;
+    P.scale = L.scale; P.shift = L.shift;
+    P.res_hi = residual ? residual->hi : nullptr; P.res_lo = residual ? residual->lo : nullptr;
+    P.out_hi = out.hi; P.out_lo = out.lo;
+    P.sat_count = c->sat_count;
+    if (L.cin2) {
+        if (L.k != 1) { set_error("fused second GEMM needs a 1x1 first convolution"); return IVOSW_ERR_INVALID; }
+        fill_tap(P.taps[0], 0, 0, 1, L.cin);
+        fill_tap(P.taps[1], 0, 0, L.stride2, L.cin2);
+    } else {
+        const int pad = L.dil * (L.k - 1) / 2;
+        for (int kh = 0; kh < L.k; ++kh)
+            for (int kw = 0; kw < L.k; ++kw)
+                fill_tap(P.taps[kh * L.k + kw], kh * L.dil - pad, kw * L.dil - pad, L.stride, L.cin);
+    }
+    if (BN == 64) return launch_tc_variant<64, 4, true>(c, maps, P, s);
+    return launch_tc_variant<128, 3, true>(c, maps, P, s);
 }
 
 // ------------------------------------------------------------------------------------------------

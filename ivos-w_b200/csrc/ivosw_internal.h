@@ -53,6 +53,20 @@ struct ConvLayer {
 
 std::vector<ConvLayer> make_resnet50_layers();
 
+// One tensor-core convolution on power-of-two canvases (the VOS encoder: manet_encoder.cu / conv_tc.cu launch_conv_tc_g)
+struct GConv {
+    int cin = 0, cout = 0;                      // multiples of 64 (zero-padded channels)
+    int k = 1, stride = 1, dil = 1;
+    int in_hp = 0, in_wp = 0, out_hp = 0, out_wp = 0;   // canvases (powers of two)
+    int valid_h = 0, valid_w = 0;               // feature-map size inside the output canvas
+    int relu = 1;
+    __half* w_hi = nullptr;                     // [cout][k*k*cin + cin2], BatchNorm scale folded in when fused
+    __half* w_lo = nullptr;
+    float* scale = nullptr;
+    float* shift = nullptr;
+    int cin2 = 0, stride2 = 1, in2_hp = 0, in2_wp = 0;   // fused 1x1 second GEMM (downsample branch)
+};
+
 // conv3 + downsample of a stage's first bottleneck as one GEMM (conv_tc.cu: launch_conv_tc with `fuse`): the concatenated,
 // BatchNorm-scaled weight [cout][cin3 + cin_d] as split-fp16 planes, scale = 1, shift = shift3 + shift_d.
 struct FusedTail {
@@ -178,6 +192,7 @@ struct ivosw_ctx {
     int stack_arena_cap = 0;
     int chunk_cap_seen = 0;
     void* stack_state = nullptr;
+    void* enc_state = nullptr;               // manet_encoder.cu
     void* train_state = nullptr;             // train.cu
     void* gather_state = nullptr;            // gather.cu: peer-memory exchange of the frame-sharded round
     bool stack_on = false;
@@ -222,8 +237,15 @@ int launch_conv_simt(ivosw_ctx* c, const ConvLayer& L, const float* in, const fl
 // ---- conv_tc.cu
 int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const SplitAct* residual, const SplitAct& out,
                    int B, int terms, cudaStream_t s, const FusedTail* fuse = nullptr, const SplitAct* in2 = nullptr);
+int launch_conv_tc_g(ivosw_ctx* c, const GConv& L, const SplitAct& in, const SplitAct* in2, const SplitAct* residual,
+                     const SplitAct& out, int out_ld, int B, int terms, cudaStream_t s);
 int launch_split(ivosw_ctx* c, const float* in, const SplitAct& out, long long n, cudaStream_t s);
 int launch_merge(ivosw_ctx* c, const SplitAct& in, float* out, long long n, int use_lo, cudaStream_t s);
+// ---- manet_encoder.cu (MANet feature extractor, restatement)
+size_t manet_encoder_blob_floats();
+int manet_encoder_load(ivosw_ctx* c, const float* blob, size_t n_floats);
+int manet_encoder_forward(ivosw_ctx* c, const float* frames, int B, int H, int W, float* out, int terms, cudaStream_t s);
+void manet_encoder_release(ivosw_ctx* c);
 // ---- train.cu (AssessNet optimisation step, config C5)
 int train_begin(ivosw_ctx* c, const float* blob, size_t n_floats);
 int train_step(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, const float* targets_dev, const int* valid_dev, float lr,

@@ -60,6 +60,9 @@ SYMBOLS = {
     "ivosw_stage_times": (C.c_int, [C.c_void_p, _c_f, C.POINTER(C.c_longlong), C.c_int]),
     "ivosw_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_i,
                                    C.c_void_p]),
+    "ivosw_manet_encoder_blob_floats": (C.c_size_t, []),
+    "ivosw_manet_encoder_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ivosw_manet_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ivosw_assess_train_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ivosw_assess_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, _c_f,

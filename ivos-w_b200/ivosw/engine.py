@@ -54,6 +54,27 @@ def pack_assess(sd):
     return out
 
 
+def pack_manet_encoder(sd):
+    """State dict of the MANet feature-extractor restatement (ivosw/manet_arch.py key names) -> flat fp32 blob
+    (ivosw_manet_encoder_load): per convolution OHWI weight, then gamma, beta, running_mean - conv bias, running_var."""
+    from . import manet_arch
+    parts = []
+    for c in manet_arch.convs():
+        w = sd[c.name + ".weight"].detach().to("cpu", torch.float32)
+        if tuple(w.shape) != (c.cout, c.cin // c.groups, c.k, c.k):
+            raise ValueError("%s.weight has shape %s" % (c.name, tuple(w.shape)))
+        parts.append(w.permute(0, 2, 3, 1).reshape(-1))
+        mean = sd[c.bn + ".running_mean"].detach().to("cpu", torch.float32)
+        if c.bias:
+            mean = mean - sd[c.name + ".bias"].detach().to("cpu", torch.float32)
+        parts += [sd[c.bn + ".weight"].detach().float().cpu(), sd[c.bn + ".bias"].detach().float().cpu(), mean,
+                  sd[c.bn + ".running_var"].detach().float().cpu()]
+    out = np.ascontiguousarray(torch.cat([p.contiguous().reshape(-1) for p in parts]).numpy(), dtype=np.float32)
+    if out.size != lib.ivosw_manet_encoder_blob_floats():
+        raise ValueError("MANet encoder blob has %d floats, library expects %d" % (out.size, lib.ivosw_manet_encoder_blob_floats()))
+    return out
+
+
 def unpack_assess(blob, template, grads=False):
     """Inverse of pack_assess: flat blob -> dict with the reference's key names (OHWI -> OIHW).  Keys the blob does not
     carry (conv1_m / conv1_n, num_batches_tracked) are taken from ``template`` (gradients: omitted)."""
@@ -342,6 +363,21 @@ class Engine:
         check(lib.ivosw_agent_action_dev(self._h, _ptr(mq_dev), _np_ptr(ann), T, _np_ptr(q), C.byref(nf),
                                          _stream(self.device)))
         return int(nf.value), q
+
+    # ------------------------------------------------------------------ MANet feature extractor (csrc/manet_encoder.cu)
+    def load_manet_encoder(self, sd):
+        blob = pack_manet_encoder(sd)
+        check(lib.ivosw_manet_encoder_load(self._h, _np_ptr(blob), blob.size))
+
+    def manet_extract_feature(self, frames):
+        """frames: B x 3 x H x W CUDA fp32 (normalised) -> B x 100 x h/4 x w/4 embedding (restatement, see manet_arch)."""
+        from . import manet_arch
+        x = self._dev32(frames)
+        B, _, H, W = x.shape
+        (_, _), (h4, w4), _, _ = manet_arch.feature_sizes(H, W)
+        out = torch.empty((B, manet_arch.EMBED_DIM, h4, w4), device=self.device, dtype=torch.float32)
+        check(lib.ivosw_manet_encoder_forward(self._h, _ptr(x), B, H, W, _ptr(out), _stream(self.device)))
+        return out
 
     # ------------------------------------------------------------------ AssessNet training step (csrc/train.cu, config C5)
     def train_begin(self, sd):

@@ -177,3 +177,31 @@ def assess_state_dict(seed=0):
     sd["fc1.weight"] = (torch.rand((1, 2048), generator=g) * 2 - 1) * bound * _ASSESS_FC_GAIN
     sd["fc1.bias"] = torch.tensor([_ASSESS_FC_BIAS])
     return sd
+
+
+def manet_encoder_state_dict(seed=0):
+    """Seeded parameters for the MANet feature extractor restatement (ivosw/manet_arch.py): He-normal convolutions,
+    BatchNorm statistics / affine parameters randomised around (0, 1), the last BatchNorm of every bottleneck scaled by
+    0.25 so that activations stay O(1) through 33 residual blocks."""
+    from . import manet_arch
+    g = torch.Generator().manual_seed(3000 + seed)
+    sd = {}
+    for c in manet_arch.convs():
+        fan = c.k * c.k * c.cout
+        sd[c.name + ".weight"] = torch.randn((c.cout, c.cin // c.groups, c.k, c.k), generator=g) * math.sqrt(2.0 / fan)
+        if c.bias:
+            sd[c.name + ".bias"] = 0.05 * torch.randn(c.cout, generator=g)
+        gain = 0.25 if c.bn.endswith("bn3") else 1.0
+        sd[c.bn + ".weight"] = (0.8 + 0.4 * torch.rand(c.cout, generator=g)) * gain
+        sd[c.bn + ".bias"] = 0.05 * torch.randn(c.cout, generator=g)
+        sd[c.bn + ".running_mean"] = 0.05 * torch.randn(c.cout, generator=g)
+        sd[c.bn + ".running_var"] = 0.8 + 0.4 * torch.rand(c.cout, generator=g)
+    return sd
+
+
+def manet_frames(seed, B, H, W):
+    """B x 3 x H x W frames as MANet's loader hands them to extract_feature (ImageNet-normalised RGB)."""
+    all_F, _, _ = make_clip(seed, B, H, W, 1)
+    mean = np.array([0.485, 0.456, 0.406], np.float32)[None, :, None, None]
+    std = np.array([0.229, 0.224, 0.225], np.float32)[None, :, None, None]
+    return ((all_F - mean) / std).astype(np.float32)
