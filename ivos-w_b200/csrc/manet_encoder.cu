@@ -123,69 +123,110 @@ __global__ void __launch_bounds__(256) enc_pool_kernel(const float* __restrict__
     st_split(hi, lo, (size_t)i, m);
 }
 
-// ------------------------------------------------------------------------------------------------ ASPP image pooling
-// mean over the feature map: x [B][Hp*Wp][C] split planes (zeros outside the map, so the sum over the canvas is the sum
-// over the map) -> gap [B][C] fp32
-__global__ void __launch_bounds__(256) enc_gap_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int use_lo, int px,
-                                                      int C, float inv_n, float* __restrict__ gap) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (c >= C) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    const size_t base = (size_t)b * px * C + c;
-    int p = 0;
-    for (; p + 3 < px; p += 4) {
-        s0 += ld_split(hi, lo, base + (size_t)p * C, use_lo); s1 += ld_split(hi, lo, base + (size_t)(p + 1) * C, use_lo);
-        s2 += ld_split(hi, lo, base + (size_t)(p + 2) * C, use_lo); s3 += ld_split(hi, lo, base + (size_t)(p + 3) * C, use_lo);
+// 8 consecutive channels of a split-fp16 tensor <-> 8 floats (one 16-byte load / store per plane)
+__device__ __forceinline__ void ld_split8(const __half* hi, const __half* lo, size_t i, bool use_lo, float* v) {
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + i);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+    uint32_t lw[4] = {0u, 0u, 0u, 0u};
+    if (use_lo) { const uint4 l = *reinterpret_cast<const uint4*>(lo + i); lw[0] = l.x; lw[1] = l.y; lw[2] = l.z; lw[3] = l.w; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[u]));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[u]));
+        v[2 * u] = fmaf(lf.x, 1.0f / 2048.0f, hf.x); v[2 * u + 1] = fmaf(lf.y, 1.0f / 2048.0f, hf.y);
     }
-    for (; p < px; ++p) s0 += ld_split(hi, lo, base + (size_t)p * C, use_lo);
-    gap[(size_t)b * C + c] = ((s0 + s1) + (s2 + s3)) * inv_n;
+}
+__device__ __forceinline__ void st_split8(__half* hi, __half* lo, size_t i, const float* v) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float a = fminf(fmaxf(v[2 * u], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * u + 1], -65504.f), 65504.f);
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+        hw[u] = *reinterpret_cast<const uint32_t*>(&h); lw[u] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(hi + i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(lo + i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
-// 1x1 convolution of the pooled vector + BatchNorm + ReLU, broadcast over the feature map (the bilinear upsampling of a
-// 1 x 1 map is a constant) into channels [coff, coff + 256) of the concatenation buffer (row pitch ld)
-__global__ void __launch_bounds__(256) enc_gap_branch_kernel(const float* __restrict__ gap, const float* __restrict__ w /*[256][2048]*/,
-                                                             const float* __restrict__ scale, const float* __restrict__ shift,
-                                                             __half* __restrict__ hi, __half* __restrict__ lo, int h, int w_, int Hp, int Wp,
-                                                             int ld, int coff) {
-    __shared__ float val[256];
-    const int b = blockIdx.y;
-    {   // every CTA recomputes the 256 outputs (2048 x 256 MACs: negligible), one per thread
-        const int co = threadIdx.x;
-        const float* g = gap + (size_t)b * 2048;
-        const float* wr = w + (size_t)co * 2048;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int k = 0; k < 2048; k += 4) {
-            a0 = fmaf(wr[k], g[k], a0); a1 = fmaf(wr[k + 1], g[k + 1], a1);
-            a2 = fmaf(wr[k + 2], g[k + 2], a2); a3 = fmaf(wr[k + 3], g[k + 3], a3);
-        }
-        val[co] = fmaxf(fmaf((a0 + a1) + (a2 + a3), scale[co], shift[co]), 0.f);
+// ------------------------------------------------------------------------------------------------ ASPP image pooling
+// partial sums over a slice of the canvas (zeros outside the map, so canvas sums are map sums):
+// x [B][px][C] split planes -> part[b][split][C] fp32; 8 channels per thread
+constexpr int GAP_SPLITS = 16;
+__global__ void __launch_bounds__(256) enc_gap_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int use_lo, int px,
+                                                      int C, float* __restrict__ part) {
+    const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int b = blockIdx.y, sp = blockIdx.z;
+    if (c8 >= C) return;
+    const int per = (px + GAP_SPLITS - 1) / GAP_SPLITS;
+    const int p0 = sp * per, p1 = min(px, p0 + per);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = p0; p < p1; ++p) {
+        float v[8];
+        ld_split8(hi, lo, ((size_t)b * px + p) * C + c8, use_lo, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[((size_t)b * GAP_SPLITS + sp) * C + c8 + k] = acc[k];
+}
+
+// pooled vector (fixed-order sum of the partials) -> 1x1 convolution + BatchNorm + ReLU: val[b][256]
+__global__ void __launch_bounds__(256) enc_gap_gemv_kernel(const float* __restrict__ part, float inv_n, const float* __restrict__ w /*[256][2048]*/,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           float* __restrict__ val) {
+    __shared__ float g[2048];
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < 2048; c += 256) {
+        float s = 0.f;
+        for (int k = 0; k < GAP_SPLITS; ++k) s += part[((size_t)b * GAP_SPLITS + k) * 2048 + c];
+        g[c] = s * inv_n;
     }
     __syncthreads();
-    const int rows_per_cta = (Hp * Wp + gridDim.x - 1) / gridDim.x;
-    const int p0 = blockIdx.x * rows_per_cta, p1 = min(Hp * Wp, p0 + rows_per_cta);
-    for (int p = p0; p < p1; ++p) {
-        const int y = p / Wp, x = p - y * Wp;
-        const float v = (y < h && x < w_) ? val[threadIdx.x] : 0.f;
-        st_split(hi, lo, ((size_t)b * Hp * Wp + p) * ld + coff + threadIdx.x, v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int co = warp; co < 256; co += 8) {                      // one warp per output channel: coalesced weight rows
+        const float* wr = w + (size_t)co * 2048;
+        float a = 0.f;
+        for (int k = lane; k < 2048; k += 32) a = fmaf(wr[k], g[k], a);
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) val[b * 256 + co] = fmaxf(fmaf(a, scale[co], shift[co]), 0.f);
     }
+}
+
+// broadcast over the feature map (the bilinear upsampling of a 1 x 1 map is a constant) into channels
+// [coff, coff + 256) of the concatenation buffer (row pitch ld); 8 channels per thread
+__global__ void __launch_bounds__(256) enc_gap_broadcast_kernel(const float* __restrict__ val, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                int h, int w_, int Hp, int Wp, int ld, int coff, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B * Hp * Wp * 32
+    if (i >= total) return;
+    const int c8 = (int)(i & 31) * 8;
+    long long p = i >> 5;
+    const int x = (int)(p % Wp); p /= Wp;
+    const int y = (int)(p % Hp);
+    const long long b = p / Hp;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (y < h && x < w_) ? val[b * 256 + c8 + k] : 0.f;
+    st_split8(hi, lo, ((size_t)(b * Hp + y) * Wp + x) * ld + coff + c8, v);
 }
 
 // ------------------------------------------------------------------------------------------------ decoder pieces
 // bilinear upsampling (align_corners=True) of a C-channel map from canvas (Hs, Ws; map hs x ws) to canvas (Hd, Wd; map
-// hd x wd), into channels [coff, coff + C) of a buffer with row pitch ld
+// hd x wd), into channels [coff, coff + C) of a buffer with row pitch ld; 8 channels per thread
 __global__ void __launch_bounds__(256) enc_upsample_kernel(const __half* __restrict__ shi, const __half* __restrict__ slo, int use_lo,
                                                            int hs, int ws, int Hs, int Ws, int hd, int wd, int Hd, int Wd, int C,
                                                            float sy, float sx, __half* __restrict__ dhi, __half* __restrict__ dlo,
                                                            int ld, int coff, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B * Hd * Wd * C
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B * Hd * Wd * C / 8
     if (i >= total) return;
-    const int c = (int)(i % C);
-    long long p = i / C;
+    const int c8n = C / 8;
+    const int c8 = (int)(i % c8n) * 8;
+    long long p = i / c8n;
     const int x = (int)(p % Wd); p /= Wd;
     const int y = (int)(p % Hd);
     const long long b = p / Hd;
-    float v = 0.f;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (y < hd && x < wd) {
         // ATen area_pixel_compute_source_index(align_corners=True): src = scale * dst
         const float fy = sy * (float)y, fx = sx * (float)x;
@@ -193,42 +234,50 @@ __global__ void __launch_bounds__(256) enc_upsample_kernel(const __half* __restr
         const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
         const float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
         const size_t base = (size_t)b * Hs * Ws;
-        const float v00 = ld_split(shi, slo, (base + (size_t)y0 * Ws + x0) * C + c, use_lo);
-        const float v01 = ld_split(shi, slo, (base + (size_t)y0 * Ws + x1) * C + c, use_lo);
-        const float v10 = ld_split(shi, slo, (base + (size_t)y1 * Ws + x0) * C + c, use_lo);
-        const float v11 = ld_split(shi, slo, (base + (size_t)y1 * Ws + x1) * C + c, use_lo);
-        v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+        float v00[8], v01[8], v10[8], v11[8];
+        ld_split8(shi, slo, (base + (size_t)y0 * Ws + x0) * C + c8, use_lo, v00);
+        ld_split8(shi, slo, (base + (size_t)y0 * Ws + x1) * C + c8, use_lo, v01);
+        ld_split8(shi, slo, (base + (size_t)y1 * Ws + x0) * C + c8, use_lo, v10);
+        ld_split8(shi, slo, (base + (size_t)y1 * Ws + x1) * C + c8, use_lo, v11);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ly0 * (lx0 * v00[k] + lx1 * v01[k]) + ly1 * (lx0 * v10[k] + lx1 * v11[k]);
     }
-    st_split(dhi, dlo, ((size_t)(b * Hd + y) * Wd + x) * ld + coff + c, v);
+    st_split8(dhi, dlo, ((size_t)(b * Hd + y) * Wd + x) * ld + coff + c8, v);
 }
 
-// depthwise 3x3 (pad 1) + BatchNorm + ReLU on a canvas (zeros outside the map = the padding); w [C][3][3]
+// depthwise 3x3 (pad 1) + BatchNorm + ReLU on a canvas (zeros outside the map = the padding); w [C][3][3];
+// 8 channels per thread
 __global__ void __launch_bounds__(256) enc_dwconv_kernel(const __half* __restrict__ shi, const __half* __restrict__ slo, int use_lo,
                                                          const float* __restrict__ w, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, int h, int w_, int Hp, int Wp, int C,
                                                          __half* __restrict__ dhi, __half* __restrict__ dlo, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B * Hp * Wp * C
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B * Hp * Wp * C / 8
     if (i >= total) return;
-    const int c = (int)(i % C);
-    long long p = i / C;
+    const int c8n = C / 8;
+    const int c8 = (int)(i % c8n) * 8;
+    long long p = i / c8n;
     const int x = (int)(p % Wp); p /= Wp;
     const int y = (int)(p % Hp);
     const long long b = p / Hp;
-    float v = 0.f;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (y < h && x < w_) {
-        float acc = 0.f;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int dy = -1; dy <= 1; ++dy) {
             const int iy = y + dy;
             if (iy < 0 || iy >= Hp) continue;
             for (int dx = -1; dx <= 1; ++dx) {
                 const int ix = x + dx;
                 if (ix < 0 || ix >= Wp) continue;
-                acc = fmaf(ld_split(shi, slo, ((size_t)(b * Hp + iy) * Wp + ix) * C + c, use_lo), w[c * 9 + (dy + 1) * 3 + dx + 1], acc);
+                float t[8];
+                ld_split8(shi, slo, ((size_t)(b * Hp + iy) * Wp + ix) * C + c8, use_lo, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(t[k], __ldg(w + (c8 + k) * 9 + (dy + 1) * 3 + dx + 1), acc[k]);
             }
         }
-        v = fmaxf(fmaf(acc, scale[c], shift[c]), 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(acc[k], scale[c8 + k], shift[c8 + k]), 0.f);
     }
-    st_split(dhi, dlo, (size_t)i, v);
+    st_split8(dhi, dlo, ((size_t)(b * Hp + y) * Wp + x) * C + c8, v);
 }
 
 // embedding [B][Hp*Wp][Cp] split planes -> [B][C][h][w] fp32 (the layout extract_feature returns)
@@ -455,7 +504,7 @@ int manet_encoder_forward(ivosw_ctx* c, const float* frames, int B, int H, int W
     const size_t o_p4 = planes(P4, 64), o_t1_4 = planes(P4, 128), o_t2_4 = planes(P4, 64), o_x4a = planes(P4, 256), o_x4b = planes(P4, 256);
     const size_t o_t1_8 = planes(P8, 256), o_t2_8 = planes(P8, 128), o_x8a = planes(P8, 512), o_x8b = planes(P8, 512);
     const size_t o_t1_16 = planes(P16, 512), o_t2_16 = planes(P16, 512), o_x16a = planes(P16, 2048), o_x16b = planes(P16, 2048);
-    const size_t o_cat16 = planes(P16, 1280), o_a16 = planes(P16, 256), o_gap = take((size_t)B * 2048 * 4);
+    const size_t o_cat16 = planes(P16, 1280), o_a16 = planes(P16, 256), o_gap = take((size_t)B * (GAP_SPLITS * 2048 + 256) * 4);
     const size_t o_cat4 = planes(P4, 320), o_d4a = planes(P4, 256), o_d4b = planes(P4, 256), o_e4 = planes(P4, 128);
     total += (size_t)64 << 20;      // slack: an 8 x 16 canvas tile of a missing second image, as in conv_tc.cu
     int rc;
@@ -535,11 +584,13 @@ int manet_encoder_forward(ivosw_ctx* c, const float* frames, int B, int H, int W
         if ((rc = launch_conv_tc_g(c, g, x, nullptr, nullptr, slice, 1280, B, terms, s))) return rc;
     }
     {
-        float* gap = (float*)(base + o_gap);
-        enc_gap_kernel<<<dim3(2048 / 256, B), 256, 0, s>>>(x.hi, x.lo, use_lo, (int)P16, 2048, 1.0f / (float)(h16 * w16), gap);
-        enc_gap_branch_kernel<<<dim3(32, B), 256, 0, s>>>(gap, E->gap_w, E->gap_scale, E->gap_shift, cat16.hi, cat16.lo, h16, w16, H16, W16,
-                                                          1280, 1024);
-        c->launches += 2;
+        float* part = (float*)(base + o_gap);                        // [B][GAP_SPLITS][2048], then val [B][256]
+        float* val = part + (size_t)B * GAP_SPLITS * 2048;
+        enc_gap_kernel<<<dim3(1, B, GAP_SPLITS), 256, 0, s>>>(x.hi, x.lo, use_lo, (int)P16, 2048, part);
+        enc_gap_gemv_kernel<<<B, 256, 0, s>>>(part, 1.0f / (float)(h16 * w16), E->gap_w, E->gap_scale, E->gap_shift, val);
+        const long long tb = (long long)B * P16 * 32;
+        enc_gap_broadcast_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, s>>>(val, cat16.hi, cat16.lo, h16, w16, H16, W16, 1280, 1024, tb);
+        c->launches += 3;
         IVOSW_CUDA(cudaGetLastError());
     }
     const SplitAct a16 = view(o_a16, P16, 256);
@@ -551,7 +602,7 @@ int manet_encoder_forward(ivosw_ctx* c, const float* frames, int B, int H, int W
     // ---- decoder: [upsampled ASPP | 48-channel shortcut] -> 3x3 -> 3x3 -> depthwise 3x3 -> 1x1 (100)
     const SplitAct cat4 = view(o_cat4, P4, 320);
     {
-        const long long tot = (long long)B * P4 * 256;
+        const long long tot = (long long)B * P4 * 256 / 8;
         const float sy = h4 > 1 ? (float)(h16 - 1) / (float)(h4 - 1) : 0.f, sx = w4 > 1 ? (float)(w16 - 1) / (float)(w4 - 1) : 0.f;
         enc_upsample_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(a16.hi, a16.lo, use_lo, h16, w16, H16, W16, h4, w4, H4, W4, 256, sy,
                                                                          sx, cat4.hi, cat4.lo, 320, 0, tot);
@@ -569,7 +620,7 @@ int manet_encoder_forward(ivosw_ctx* c, const float* frames, int B, int H, int W
         GConv g2 = E->convs[ci++];                                       // last_conv.4
         g2.in_hp = H4; g2.in_wp = W4; g2.out_hp = H4; g2.out_wp = W4; g2.valid_h = h4; g2.valid_w = w4;
         if ((rc = launch_conv_tc_g(c, g2, d4a, nullptr, nullptr, d4b, 256, B, terms, s))) return rc;
-        const long long tot = (long long)B * P4 * 256;
+        const long long tot = (long long)B * P4 * 256 / 8;
         enc_dwconv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d4b.hi, d4b.lo, use_lo, E->dw_w, E->dw_scale, E->dw_shift, h4, w4, H4, W4,
                                                                        256, d4a.hi, d4a.lo, tot);
         c->launches += 1;
