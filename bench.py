@@ -25,9 +25,18 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: if the environment asks NCCL for a banner (NCCL_DEBUG=VERSION/WARN/INFO print
-# "NCCL version ..." on stdout by default), send NCCL's own log to stderr instead
+# stdout carries exactly one JSON line.  Native libraries write to file descriptor 1 on their own (NCCL prints a
+# "NCCL version ..." banner there when its first communicator is created), so fd 1 is pointed at stderr for the whole run
+# and the JSON line goes to a private duplicate of the original stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(REPO, "ivos-w_b200")
@@ -278,7 +287,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -481,7 +490,7 @@ def run_ours(args):
             line["ref_gpu_pytorch"] = ref_gpu_pytorch_leg(clips[0], ms_per_step, e2e_ms)
         except Exception as ex:            # the leg is a comparison, never a reason to lose the bench line
             line["ref_gpu_pytorch"] = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
