@@ -265,7 +265,12 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stack_kernel(const __grid_
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
                         const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-                        if (x3) {
+                        if (x3 && k == TC_BK / 16 - 1) {
+                            // last K step: the longer instruction last, like conv_tc.cu (same accumulation order:
+                            // the two kernels stay bit-identical)
+                            umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+                            umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, 1u);
+                        } else if (x3) {
                             umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, accum);   // [D0 | D1] += A_hi [W_hi ; W_lo]^T
                             umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);         //       D1  += A_lo  W_hi^T
                         } else {

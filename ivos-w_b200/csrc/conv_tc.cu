@@ -193,10 +193,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // ====================================== MMA issuer ======================================
         // The whole warp walks the loop with warp-uniform values and elect.sync picks the issuing lane: descriptors
         // and barrier addresses then live in uniform registers and every UTCHMMA / UTCBAR issues straight, without
-        // the ELECT / BRA.U.ANY waterfall ptxas wraps around per-thread operands.  tcgen05.mma issue is close to
-        // synchronous (scripts/umma_rate.cu: any result-consuming instruction between two bursts shows up as a
-        // tensor-pipe bubble), so the instruction stream between the last MMA of a block and the first of the next
-        // is kept as short as possible.
+        // the ELECT / BRA.U.ANY waterfall ptxas wraps around per-thread operands.
         {
             // instruction descriptor: D = F32, A = B = F16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -206,43 +203,66 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t smem_base = smem_u32(smem);
             int stage = 0; uint32_t full_bits = 0;               // parity of the next operand block, per slot
             int acc = 0; uint32_t acc_phase = 0;
+            // Between two bursts the tensor pipe only has the last instruction of the previous burst queued (64-128
+            // cycles of work): everything the issuing thread does from "block landed" to the first MMA of the next burst
+            // is a pipe bubble (scripts/umma_rate2.cu: 896 cycles per K block with a wait between bursts, 775 free
+            // running).  So (1) the NEXT block's barrier is probed, without blocking, before the last K step of the
+            // current burst — when the loads keep up, the next burst starts without any wait in between (797 cycles);
+            // (2) the last K step issues its N = BN instruction first and the N = 2 BN one last; (3) descriptors are
+            // one add away from a per-kernel constant.
+            const uint64_t desc0 = make_sw128_desc(smem_base);   // A_hi of slot 0; everything else is + constant
+            constexpr uint32_t SLOT16 = S::STAGE_BYTES >> 4, ALO16 = S::A_BYTES >> 4, B16 = (2 * S::A_BYTES) >> 4;
+            bool ready = false;                                  // the probe already saw the next block
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
                 const uint32_t d1 = d0 + BN;
+                const bool last_tile = tile + (int)gridDim.x >= num_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], (full_bits >> stage) & 1u);
+                    if (!ready) mbar_wait(&full_bar[stage], (full_bits >> stage) & 1u);
                     full_bits ^= 1u << stage;
                     tc_fence_after();
-                    const uint32_t st = smem_base + (uint32_t)(stage * S::STAGE_BYTES);
-                    const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + S::A_BYTES);
-                    const uint64_t b_hi = make_sw128_desc(st + 2 * S::A_BYTES);
+                    const uint64_t a_hi = desc0 + (uint64_t)((uint32_t)stage * SLOT16);
+                    const uint64_t a_lo = a_hi + ALO16, b_hi = a_hi + B16;
+                    const bool last_kb = kb == num_kb - 1;
+                    if (!no_mma && elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16 - 1; ++k) {
+                            const uint64_t adv = (uint64_t)(2 * k);                  // +32 bytes inside the swizzle row
+                            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                            if (x3) {
+                                // [D0 | D1] += A_hi * [W_hi ; W_lo]^T as ONE N = 2*BN instruction (the two weight
+                                // tiles are contiguous in the stage, the two accumulators contiguous in TMEM):
+                                // A_hi is read from shared memory once instead of twice
+                                umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, accum);
+                                umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+                            } else {
+                                umma_f16(d0, a_hi + adv, b_hi + adv, idesc, accum);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // where the next operand block sits: the slot after this one, one further at the end of a tile
+                    // that carries a residual block
+                    int nstage = stage + 1 == S::STAGES ? 0 : stage + 1;
+                    if (last_kb && skip_res_slot) nstage = nstage + 1 == S::STAGES ? 0 : nstage + 1;
+                    ready = !(last_kb && last_tile) && mbar_test(&full_bar[nstage], (full_bits >> nstage) & 1u);
                     if (elect_one()) {
                         if (!no_mma) {
-#pragma unroll
-                            for (int k = 0; k < TC_BK / 16; ++k) {
-                                const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // +32 bytes inside the swizzle row
-                                const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-                                if (x3) {
-                                    // [D0 | D1] += A_hi * [W_hi ; W_lo]^T as ONE N = 2*BN instruction (the two weight
-                                    // tiles are contiguous in the stage, the two accumulators contiguous in TMEM):
-                                    // A_hi is read from shared memory once instead of twice
-                                    umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, accum);
-                                    umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
-                                } else {
-                                    umma_f16(d0, a_hi + adv, b_hi + adv, idesc, accum);
-                                }
+                            const uint64_t adv = (uint64_t)(2 * (TC_BK / 16 - 1));
+                            if (x3) {
+                                umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+                                umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, 1u);
+                            } else {
+                                umma_f16(d0, a_hi + adv, b_hi + adv, idesc, 1u);
                             }
                         }
                         umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
-                        if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                        if (last_kb) umma_commit(&tfull_bar[acc]);
                     }
                     __syncwarp();
-                    if (++stage == S::STAGES) stage = 0;
-                }
-                if (skip_res_slot) {                             // step over the residual block's ring position
-                    if (++stage == S::STAGES) stage = 0;
+                    stage = nstage;
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
