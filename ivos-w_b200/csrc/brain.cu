@@ -18,7 +18,7 @@
 // Latency-bound (2T dependent steps); weights are 724 KB and stay in L2 / on chip.
 #include <cooperative_groups.h>
 
-#include "ivosw_internal.h"
+#include "tc_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -53,6 +53,15 @@ __global__ void __launch_bounds__(512) brain_inproj_kernel(const float* __restri
     const int t = blockIdx.x, n = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float x0 = state[((long long)n * T + t) * 2 + 0], x1 = state[((long long)n * T + t) * 2 + 1];
+    // Every warp owns rows warp, warp + 16, ...: the weight rows of a batch of 8 are fetched before any of them is used
+    // (eight independent 512-byte row reads in flight per warp instead of one L2 round trip per row); the per-row
+    // arithmetic and its order are unchanged.
+    float wv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float* w = P + P_FC2W + (warp + 16 * i) * 128;
+        wv[i][0] = w[lane]; wv[i][1] = w[lane + 32]; wv[i][2] = w[lane + 64]; wv[i][3] = w[lane + 96];
+    }
     if (threadIdx.x < 128) {
         int j = threadIdx.x;
         float v = fmaf(P[P_FC1W + 2 * j + 1], x1, fmaf(P[P_FC1W + 2 * j], x0, 0.f)) + P[P_FC1B + j];
@@ -61,23 +70,48 @@ __global__ void __launch_bounds__(512) brain_inproj_kernel(const float* __restri
     }
     __syncthreads();
     const float a0 = sa[lane], a1 = sa[lane + 32], a2 = sa[lane + 64], a3 = sa[lane + 96];
-    for (int j = warp; j < 128; j += 16) {
-        const float* w = P + P_FC2W + j * 128;
-        float v = w[lane] * a0 + w[lane + 32] * a1 + w[lane + 64] * a2 + w[lane + 96] * a3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = warp + 16 * i;
+        float v = wv[i][0] * a0 + wv[i][1] * a1 + wv[i][2] * a2 + wv[i][3] * a3;
         v = warp_sum(v);
         if (lane == 0) {
             se[j] = v + P[P_FC2B + j];   // no ReLU after fc2 (agent.py:46)
             if (Esave) Esave[((long long)n * T + t) * 128 + j] = se[j];
         }
     }
+    // first batch of W_ih rows: independent of e, in flight across the barrier
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float* w = P + P_WIH + (warp + 16 * i) * 128;
+        wv[i][0] = w[lane]; wv[i][1] = w[lane + 32]; wv[i][2] = w[lane + 64]; wv[i][3] = w[lane + 96];
+    }
     __syncthreads();
     const float e0 = se[lane], e1 = se[lane + 32], e2 = se[lane + 64], e3 = se[lane + 96];
     float* gi = GI + ((long long)n * T + t) * 512;
-    for (int j = warp; j < 512; j += 16) {
-        const float* w = P + P_WIH + j * 128;
-        float v = w[lane] * e0 + w[lane + 32] * e1 + w[lane + 64] * e2 + w[lane + 96] * e3;
-        v = warp_sum(v);
-        if (lane == 0) gi[j] = v;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        float wn[8][4];
+        if (b < 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float* w = P + P_WIH + (warp + 16 * ((b + 1) * 8 + i)) * 128;
+                wn[i][0] = w[lane]; wn[i][1] = w[lane + 32]; wn[i][2] = w[lane + 64]; wn[i][3] = w[lane + 96];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = warp + 16 * (b * 8 + i);
+            float v = wv[i][0] * e0 + wv[i][1] * e1 + wv[i][2] * e2 + wv[i][3] * e3;
+            v = warp_sum(v);
+            if (lane == 0) gi[j] = v;
+        }
+        if (b < 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wv[i][q] = wn[i][q];
+        }
     }
 }
 
@@ -166,7 +200,9 @@ __global__ void brain_pack_d1t_kernel(const float* __restrict__ w, float* __rest
 }
 
 __global__ void brain_decode8_kernel(const float* __restrict__ P, const float4* __restrict__ d1t,
-                                     const float* __restrict__ Hout, int T, float* __restrict__ Q, int* __restrict__ argmax);
+                                     const float* __restrict__ Hout, int T, float* __restrict__ Q, int* __restrict__ argmax,
+                                     unsigned int* __restrict__ done_count);
+constexpr int DEC_MAX_SEQ = 65536;      // sequences per launch (one completion counter each)
 
 int brain_pack(ivosw_ctx* c) {
     if (!c->brain_whh_t) IVOSW_CUDA(cudaMalloc(&c->brain_whh_t, sizeof(float4) * 32 * 512));
@@ -178,7 +214,11 @@ int brain_pack(ivosw_ctx* c) {
     const int rec_smem = 16 * 512 * 16 + (512 + 128) * 4;
     IVOSW_CUDA(cudaFuncSetAttribute(brain_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_smem));
     IVOSW_CUDA(cudaFuncSetAttribute(brain_decode8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (256 * 128 + 8 * 256 * 8 + 8 * 4 * 8) * 4));
+                                    (256 * 128 + 256 * 8 + 4 * 8) * 4));
+    if (!c->brain_done_count) {
+        IVOSW_CUDA(cudaMalloc(&c->brain_done_count, sizeof(unsigned int) * DEC_MAX_SEQ));
+        IVOSW_CUDA(cudaMemset(c->brain_done_count, 0, sizeof(unsigned int) * DEC_MAX_SEQ));
+    }
     IVOSW_CUDA(cudaDeviceSynchronize());
     return IVOSW_OK;
 }
@@ -252,68 +292,85 @@ brain_recurrent_cluster_kernel(const float* __restrict__ P, const float* __restr
     }
 }
 
-// Decoder + argmax, register-blocked over 8 frames per thread: 1024 threads = 8 groups x 128 decoder units,
-// a group handles 8 frames at a time so every weight read from shared memory feeds 8 FMAs.
-__global__ void __launch_bounds__(1024, 1) brain_decode8_kernel(const float* __restrict__ P,
-                                                                const float4* __restrict__ d1t,
-                                                                const float* __restrict__ Hout,  // [N][2][T][128]
-                                                                int T, float* __restrict__ Q,     // [N][T]
-                                                                int* __restrict__ argmax) {
-    extern __shared__ __align__(16) float sm[];
+// Decoder + argmax.  One CTA of 128 threads (= the 128 decoder units) per group of 8 frames: every weight read from
+// shared memory feeds 8 FMAs, the 128 KB weight image arrives as four bulk copies (one elected thread, overlapped with
+// the loads of the hidden states), and the groups of a sequence run on different SMs instead of queueing on one CTA's
+// shared-memory pipe.  The CTA that finishes last (one atomic counter per sequence) takes the arg-max over t, first
+// maximum wins (numpy semantics).  Per-output arithmetic and its order are those of the single-CTA version.
+constexpr int DEC_SMEM_BYTES = (256 * 128 + 256 * 8 + 4 * 8) * 4;
+__global__ void __launch_bounds__(128, 1) brain_decode8_kernel(const float* __restrict__ P,
+                                                               const float4* __restrict__ d1t,
+                                                               const float* __restrict__ Hout,  // [N][2][T][128]
+                                                               int T, float* __restrict__ Q,     // [N][T]
+                                                               int* __restrict__ argmax,
+                                                               unsigned int* __restrict__ done_count) {   // [N], zero between launches
+    extern __shared__ __align__(128) float sm[];
     float* sWt = sm;                              // [256][128]
-    float* ssb = sWt + 256 * 128;                 // [8 groups][256][8 frames]
-    float* sred = ssb + 8 * 256 * 8;              // [8 groups][4 warps][8 frames]
-    const int n = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < 128 * 256 / 4; i += 1024) reinterpret_cast<float4*>(sWt)[i] = __ldg(d1t + i);
-    const int grp = tid >> 7, j = tid & 127, wig = (tid >> 5) & 3, lane = tid & 31;
+    float* ss = sWt + 256 * 128;                  // [256][8 frames]
+    float* sred = ss + 256 * 8;                   // [4 warps][8 frames]
+    __shared__ uint64_t wbar;
+    __shared__ int is_last;
+    const int grp = blockIdx.x, n = blockIdx.y, j = threadIdx.x, wig = j >> 5, lane = j & 31;
+    if (j == 0) { mbar_init(&wbar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (j == 0) {
+        mbar_expect_tx(&wbar, 256 * 128 * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sWt + i * 8192)), "l"(reinterpret_cast<const float*>(d1t) + i * 8192), "r"(32768),
+                           "r"(smem_u32(&wbar)) : "memory");
+    }
     const float b1 = P[P_D1B + j], w2 = P[P_D2W + j], b2 = P[P_D2B];
     const float* hf = Hout + ((long long)n * 2 + 0) * T * 128;
     const float* hb = Hout + ((long long)n * 2 + 1) * T * 128;
-    float* ss = ssb + grp * 256 * 8;
-    for (int t0 = 0; t0 < T; t0 += 64) {          // uniform trip count: every thread reaches every barrier
-        const int tb = t0 + grp * 8;
-        float vf[8], vb[8];
+    const int tb = grp * 8;
+    float vf[8], vb[8];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) {
-            const int t = tb + f;
-            vf[f] = t < T ? fmaxf(hf[(long long)t * 128 + j], 0.f) : 0.f;
-            vb[f] = t < T ? fmaxf(hb[(long long)t * 128 + j], 0.f) : 0.f;
-        }
-        __syncthreads();                          // previous pass finished reading ss / sred
-        reinterpret_cast<float4*>(ss + j * 8)[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
-        reinterpret_cast<float4*>(ss + j * 8)[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
-        reinterpret_cast<float4*>(ss + (128 + j) * 8)[0] = make_float4(vb[0], vb[1], vb[2], vb[3]);
-        reinterpret_cast<float4*>(ss + (128 + j) * 8)[1] = make_float4(vb[4], vb[5], vb[6], vb[7]);
-        __syncthreads();
-        float acc[8];
+    for (int f = 0; f < 8; ++f) {
+        const int t = tb + f;
+        vf[f] = t < T ? fmaxf(hf[(long long)t * 128 + j], 0.f) : 0.f;
+        vb[f] = t < T ? fmaxf(hb[(long long)t * 128 + j], 0.f) : 0.f;
+    }
+    reinterpret_cast<float4*>(ss + j * 8)[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
+    reinterpret_cast<float4*>(ss + j * 8)[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
+    reinterpret_cast<float4*>(ss + (128 + j) * 8)[0] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    reinterpret_cast<float4*>(ss + (128 + j) * 8)[1] = make_float4(vb[4], vb[5], vb[6], vb[7]);
+    __syncthreads();
+    mbar_wait(&wbar, 0);                          // weight image landed
+    float acc[8];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) acc[f] = b1;
+    for (int f = 0; f < 8; ++f) acc[f] = b1;
 #pragma unroll 4
-        for (int k = 0; k < 256; ++k) {
-            const float wv = sWt[k * 128 + j];
-            const float4 s0 = reinterpret_cast<const float4*>(ss + k * 8)[0];
-            const float4 s1 = reinterpret_cast<const float4*>(ss + k * 8)[1];
-            acc[0] = fmaf(wv, s0.x, acc[0]); acc[1] = fmaf(wv, s0.y, acc[1]);
-            acc[2] = fmaf(wv, s0.z, acc[2]); acc[3] = fmaf(wv, s0.w, acc[3]);
-            acc[4] = fmaf(wv, s1.x, acc[4]); acc[5] = fmaf(wv, s1.y, acc[5]);
-            acc[6] = fmaf(wv, s1.z, acc[6]); acc[7] = fmaf(wv, s1.w, acc[7]);
-        }
+    for (int k = 0; k < 256; ++k) {
+        const float wv = sWt[k * 128 + j];
+        const float4 s0 = reinterpret_cast<const float4*>(ss + k * 8)[0];
+        const float4 s1 = reinterpret_cast<const float4*>(ss + k * 8)[1];
+        acc[0] = fmaf(wv, s0.x, acc[0]); acc[1] = fmaf(wv, s0.y, acc[1]);
+        acc[2] = fmaf(wv, s0.z, acc[2]); acc[3] = fmaf(wv, s0.w, acc[3]);
+        acc[4] = fmaf(wv, s1.x, acc[4]); acc[5] = fmaf(wv, s1.y, acc[5]);
+        acc[6] = fmaf(wv, s1.z, acc[6]); acc[7] = fmaf(wv, s1.w, acc[7]);
+    }
 #pragma unroll
-        for (int f = 0; f < 8; ++f) {
-            const float part = warp_sum(w2 * fmaxf(acc[f], 0.f));
-            if (lane == 0) sred[(grp * 4 + wig) * 8 + f] = part;
-        }
-        __syncthreads();
-        if (j < 8 && tb + j < T) {
-            const float* rp = sred + grp * 32 + j;
-            Q[(long long)n * T + tb + j] = ((rp[0] + rp[8]) + (rp[16] + rp[24])) + b2;
-        }
+    for (int f = 0; f < 8; ++f) {
+        const float part = warp_sum(w2 * fmaxf(acc[f], 0.f));
+        if (lane == 0) sred[wig * 8 + f] = part;
     }
     __syncthreads();
-    if (argmax && tid < 32) {   // first maximum wins (numpy argmax)
+    if (j < 8 && tb + j < T) {
+        const float* rp = sred + j;
+        Q[(long long)n * T + tb + j] = ((rp[0] + rp[8]) + (rp[16] + rp[24])) + b2;
+    }
+    if (argmax == nullptr) return;
+    __threadfence();                              // this group's Q values before the counter
+    __syncthreads();
+    if (j == 0) is_last = atomicAdd(done_count + n, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && j < 32) {   // first maximum wins (numpy argmax)
+        __threadfence();
         float best = -INFINITY; int bi = 0x7fffffff;
         for (int t = lane; t < T; t += 32) {
-            float v = Q[(long long)n * T + t];
+            float v = __ldcg(Q + (long long)n * T + t);
             if (v > best) { best = v; bi = t; }
         }
 #pragma unroll
@@ -322,7 +379,7 @@ __global__ void __launch_bounds__(1024, 1) brain_decode8_kernel(const float* __r
             int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if (lane == 0) argmax[n] = (bi == 0x7fffffff) ? 0 : bi;
+        if (lane == 0) { argmax[n] = (bi == 0x7fffffff) ? 0 : bi; done_count[n] = 0u; }
     }
 }
 
@@ -344,8 +401,10 @@ int launch_brain_ex(ivosw_ctx* c, const float* params, const float* whh_pack, co
                                                                  sv->G, sv->C, sv->HP);
     }
     IVOSW_CUDA(cudaGetLastError());
-    const int dec8_smem = (256 * 128 + 8 * 256 * 8 + 8 * 4 * 8) * 4;
-    brain_decode8_kernel<<<N, 1024, dec8_smem, s>>>(params, (const float4*)d1t, hout, T, q, argmax);
+    if (N > DEC_MAX_SEQ) { set_error("Brain: more than 65536 sequences per call"); return IVOSW_ERR_INVALID; }
+    if (!c->brain_done_count) { set_error("Brain weights not loaded"); return IVOSW_ERR_STATE; }
+    brain_decode8_kernel<<<dim3((T + 7) / 8, N), 128, DEC_SMEM_BYTES, s>>>(params, (const float4*)d1t, hout, T, q, argmax,
+                                                                          c->brain_done_count);
     IVOSW_CUDA(cudaGetLastError());
     c->launches += 3;
     return IVOSW_OK;

@@ -459,6 +459,7 @@ void ivosw_destroy(ivosw_ctx* c) {
     if (c->brain_params) cudaFree(c->brain_params);
     if (c->brain_whh_t) cudaFree(c->brain_whh_t);
     if (c->brain_d1t) cudaFree(c->brain_d1t);
+    if (c->brain_done_count) cudaFree(c->brain_done_count);
     if (c->target_params) cudaFree(c->target_params);
     if (c->target_whh_t) cudaFree(c->target_whh_t);
     if (c->target_d1t) cudaFree(c->target_d1t);

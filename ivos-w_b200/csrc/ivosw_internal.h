@@ -121,6 +121,7 @@ struct ivosw_ctx {
     bool brain_loaded = false;
     float* brain_params = nullptr;   // canonical order, see header
     float* brain_d1t = nullptr;      // decoder_fc1.weight transposed [256][128]
+    unsigned int* brain_done_count = nullptr;   // per-sequence completion counters of the decoder groups (zero at rest)
     float* brain_whh_t = nullptr;    // weight_hh transposed/packed for the recurrent kernel
     ivosw::DeviceBuffer brain_gi, brain_h, brain_state, brain_q, brain_arg;
     // Double-DQN training step (dqn.cu): target network, Adam moments, saved activations

@@ -276,6 +276,97 @@ __global__ void __launch_bounds__(THREADS, 1) rate_kernel_opt(int iters, long lo
     }
 }
 
+// Mode 14: the optimised ring of mode 11 fed by REAL loads: a producer thread streams LOAD_BYTES per K block from an
+// L2-resident global buffer into the slot (cp.async.bulk, 16 KB pieces, completion on full[slot]) after waiting for
+// empty[slot].  64 KB per block is what the conv kernel loads; 48 / 32 KB model designs that deliver fewer bytes per SM.
+template <int LOAD_BYTES>
+__global__ void __launch_bounds__(THREADS, 1) rate_kernel_fed(int iters, long long* cycles, const uint8_t* gsrc, int region) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ Bars B;
+    for (int i = threadIdx.x; i < SLOTS * STAGE / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = 0x2c002c00u ^ (uint32_t)(i * 2654435761u & 0x03ff03ffu);
+    if (threadIdx.x == 0) {
+        mb_init(&B.done[0], 1);
+        for (int i = 0; i < SLOTS; ++i) { mb_init(&B.full[0][i], 1); mb_init(&B.empty[0][i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&B.tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = B.tmem_slot;
+    const uint32_t idesc_256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t0 = clock64();
+    if (warp == 0) {
+        const uint64_t base = sw128_desc(s_u32(smem));
+        uint32_t ph = 0; bool ready = false;
+        for (int it0 = 0; it0 < iters; it0 += SLOTS) {
+#pragma unroll
+            for (int slot = 0; slot < SLOTS; ++slot) {
+                const int it = it0 + slot;
+                if (it < iters) {
+                    if (!ready) mb_wait(&B.full[0][slot], ph);
+                    fence_after();
+                    const uint64_t a_hi = base + (uint64_t)((slot * STAGE) >> 4), a_lo = a_hi + (A_BYTES >> 4), b = a_hi + (2 * A_BYTES >> 4);
+                    const uint32_t d0 = tmem + (uint32_t)((it & 1) * 256);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            mma(d0, a_hi + 2 * k, b + 2 * k, idesc_256, (it > 1 || k > 0) ? 1u : 0u);
+                            mma(d0 + 128, a_lo + 2 * k, b + 2 * k, idesc_128, 1u);
+                        }
+                    }
+                    __syncwarp();
+                    const int nslot = (slot + 1) % SLOTS;
+                    ready = (it + 1 < iters) && mb_test(&B.full[0][nslot], nslot == 0 ? ph ^ 1 : ph);
+                    if (elect_one()) {
+                        mma(d0 + 128, a_lo + 6, b + 6, idesc_128, 1u);
+                        mma(d0, a_hi + 6, b + 6, idesc_256, 1u);
+                        commit(&B.empty[0][slot]);
+                        if (it == iters - 1) commit(&B.done[0]);
+                    }
+                    __syncwarp();
+                }
+            }
+            ph ^= 1;
+        }
+    } else if (warp == 1 && lane == 0) {
+        int slot = 0; uint32_t ph = 0;
+        const uint8_t* src = gsrc + (size_t)blockIdx.x * region;
+        uint32_t off = 0;
+        for (int it = 0; it < iters; ++it) {
+            mb_wait(&B.empty[0][slot], ph ^ 1);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&B.full[0][slot])), "r"(LOAD_BYTES) : "memory");
+#pragma unroll
+            for (int c = 0; c < LOAD_BYTES / CP_CHUNK; ++c) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(s_u32(smem + slot * STAGE + c * CP_CHUNK)), "l"(src + off), "r"(CP_CHUNK), "r"(s_u32(&B.full[0][slot])) : "memory");
+                off += CP_CHUNK; if (off >= (uint32_t)region) off = 0;
+            }
+            if (++slot == SLOTS) { slot = 0; ph ^= 1; }
+        }
+    }
+    if (warp == 0) {
+        mb_wait(&B.done[0], 0);
+        fence_after();
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 template <int MODE>
@@ -336,6 +427,32 @@ static void run_opt(const char* what, int iters, int sms) {
     CK(cudaFree(cyc));
 }
 
+template <int LOAD_BYTES>
+static void run_fed(int iters, int sms, const uint8_t* gsrc, int region) {
+    const int smem = SLOTS * STAGE + 2048;
+    CK(cudaFuncSetAttribute(rate_kernel_fed<LOAD_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    long long* cyc;
+    CK(cudaMalloc(&cyc, sizeof(long long) * sms));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        rate_kernel_fed<LOAD_BYTES><<<sms, THREADS, smem>>>(iters, cyc, gsrc, region);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    long long h0;
+    CK(cudaMemcpy(&h0, cyc, sizeof h0, cudaMemcpyDeviceToHost));
+    const double flops = 4.0 * (2.0 * 128 * 256 * 16 + 2.0 * 128 * 128 * 16) * iters * sms;
+    printf("mode 14 optimised ring fed by bulk loads, %2d KB per K block, %4d KB region per CTA %8.3f ms %6.0f TFLOP/s %7.1f cycles/K-block  load %.1f B/clk/SM\n",
+           LOAD_BYTES / 1024, region / 1024, best, flops / best * 1e-9, (double)h0 / iters, (double)LOAD_BYTES * iters / (double)h0);
+    CK(cudaFree(cyc));
+}
+
 int main() {
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
@@ -358,5 +475,16 @@ int main() {
     run<10>("two issuing warps + bulk copies", iters, sms, gsrc);
     run_opt<true>("ring handshake, unrolled slots, N=256 last, early test", iters, sms);
     run_opt<false>("ring handshake, unrolled slots, N=256 last", iters, sms);
+    {
+        uint8_t* big;
+        const int region = 512 * 1024;                      // 148 x 512 KB = 74 MB: L2-resident
+        CK(cudaMalloc(&big, (size_t)sms * region));
+        CK(cudaMemset(big, 0x2c, (size_t)sms * region));
+        run_fed<65536>(iters, sms, big, region);
+        run_fed<49152>(iters, sms, big, region);
+        run_fed<32768>(iters, sms, big, region);
+        run_fed<16384>(iters, sms, big, region);
+        run_fed<65536>(iters, sms, big, 192 * 1024);
+    }
     return 0;
 }
