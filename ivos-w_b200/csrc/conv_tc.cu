@@ -67,10 +67,12 @@ struct TcParams {
 // read it; with 2 or 4 K blocks per tile on a 3-slot ring that serialised every tile on one residual
 // round trip.  A version with per-thread residual loads from global memory was 2x slower on res2:
 // 32 rows x 16 bytes per warp instruction is the uncoalesced pattern.  profiles/r1_tc_ceiling.md.)
-template <int BN, int STAGES_, bool STAGED_>
+// PAIR_: two CTAs of a cluster share one M = 256 MMA (cta_group::2); a CTA then stages its own 128 A rows and HALF of
+// each weight plane (BN / 2 rows): 48 instead of 64 KB per K block, and a fourth ring slot fits.
+template <int BN, int STAGES_, bool STAGED_, bool PAIR_ = false>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
-    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int B_BYTES = (PAIR_ ? BN / 2 : BN) * TC_BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = STAGES_;
     static constexpr int STG_OFF = STAGES * STAGE_BYTES;                 // 1024-byte aligned (128B swizzle atom)
@@ -86,10 +88,10 @@ struct TcMaps {
     CUtensorMap r_hi, r_lo, o_hi, o_lo;       // residual in / output (STAGED epilogue only)
 };
 
-template <int BN, int STAGES_, bool STAGED_>
+template <int BN, int STAGES_, bool STAGED_, bool PAIR_ = false>
 __global__ void __launch_bounds__(tc_threads(STAGED_), 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
-    using S = TcSmem<BN, STAGES_, STAGED_>;
+    using S = TcSmem<BN, STAGES_, STAGED_, PAIR_>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -98,10 +100,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint64_t* tfull_bar = bars + 2 * S::STAGES;      // [2]
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
-    uint64_t* res_full = bars + 2 * S::STAGES + 5;   // [2] residual block of tile t landed (t & 1)
+    // residual blocks of tile t landed: [(t & 1) * RES_BLOCKS + block].  A residual tile is 64 KB (BN = 128): one ring block,
+    // or — in the pair variant, whose slots are 48 KB — one block per 64-column half
+    constexpr int RES_BLOCKS = PAIR_ ? BN / 64 : 1;
+    constexpr int RES_G = (BN / 64) / RES_BLOCKS;      // 64-column halves per block
+    uint64_t* res_full = bars + 2 * S::STAGES + 5;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = P.tiles_m * P.tiles_n;
+    // PAIR_: a work item is a pair of neighbouring M tiles (256 pixels) x one N tile; CTA rank r of the cluster owns the
+    // A rows, the TMEM lanes and the epilogue of M tile 2 * (item / tiles_n) + r.  The host guarantees tiles_m is even.
+    const uint32_t cta_rank = PAIR_ ? cluster_ctarank() : 0u;
+    const int tile_first = PAIR_ ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR_ ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_tiles = PAIR_ ? (P.tiles_m >> 1) * P.tiles_n : P.tiles_m * P.tiles_n;
     const int num_kb = P.num_kb;
     const bool x3 = P.terms == 3;
     constexpr uint32_t TMEM_COLS = 4 * BN;           // 2 accumulator stages x (D0, D1)
@@ -110,18 +121,25 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
         for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], tc_epi_warps(STAGED_));
-            mbar_init(&res_full[i], 1);
+            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], tc_epi_warps(STAGED_) * (PAIR_ ? 2 : 1));
+            for (int r = 0; r < RES_BLOCKS; ++r) mbar_init(&res_full[i * RES_BLOCKS + r], 1);
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR_) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR_) cluster_sync_all();     // the peer's barriers exist before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
@@ -137,8 +155,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t tx_bytes = x3 ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
             const int pix_per_img = P.out_hw * P.out_wp;
             int t_local = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int nt = tile % P.tiles_n, mt = (tile / P.tiles_n) * (PAIR_ ? 2 : 1) + (int)cta_rank;
                 const int m0 = mt * TC_BM;
                 const int n_img = m0 / pix_per_img;
                 const int rem0 = m0 - n_img * pix_per_img;
@@ -155,17 +173,31 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * S::STAGE_BYTES;
                     if (P.dbg & 1) {          // measurement: MMA + epilogue only
-                        mbar_arrive(&full_bar[stage]);
+                        if (!PAIR_ || cta_rank == 0) mbar_arrive(&full_bar[stage]);
                         if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    mbar_expect_tx(&full_bar[stage], tx_bytes);
                     const int c0 = tp.c_add + cb * TC_BK;
-                    tma_load_5d(st, mh, &full_bar[stage], c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
-                    tma_load_2d(st + 2 * S::A_BYTES, &maps.w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
-                    if (x3) {
-                        tma_load_5d(st + S::A_BYTES, ml, &full_bar[stage], c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
-                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
+                    if constexpr (PAIR_) {
+                        // both CTAs' boxes complete on the LEADER's barrier (the leader issues the MMAs and arms it for the
+                        // bytes of both); this CTA's half of the weight planes: rows [rank * BN / 2, + BN / 2) of the N tile
+                        const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
+                        const int wrow = nt * BN + (int)cta_rank * (BN / 2);
+                        tma_load_5d_pair(st, mh, fb, c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                        tma_load_2d_pair(st + 2 * S::A_BYTES, &maps.w_hi, fb, kb * TC_BK, wrow);
+                        if (x3) {
+                            tma_load_5d_pair(st + S::A_BYTES, ml, fb, c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                            tma_load_2d_pair(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, fb, kb * TC_BK, wrow);
+                        }
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        tma_load_5d(st, mh, &full_bar[stage], c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                        tma_load_2d(st + 2 * S::A_BYTES, &maps.w_hi, &full_bar[stage], kb * TC_BK, nt * BN);
+                        if (x3) {
+                            tma_load_5d(st + S::A_BYTES, ml, &full_bar[stage], c0, w0 + tp.w_add, tp.p, h0 + tp.h_add, n_img);
+                            tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &maps.w_lo, &full_bar[stage], kb * TC_BK, nt * BN);
+                        }
                     }
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -174,16 +206,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         // residual block of this tile: both column halves, hi/lo planes; completion goes to
                         // res_full — the slot's own full barrier is not involved (the MMA issuer keeps a parity
                         // bit per slot and only counts the uses it waits on)
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* st = smem + stage * S::STAGE_BYTES;
-                        uint64_t* rb = &res_full[t_local & 1];
-                        mbar_expect_tx(rb, (x3 ? 2u : 1u) * (BN / 64) * TC_BM * 128);
 #pragma unroll
-                        for (int g = 0; g < BN / 64; ++g) {
-                            tma_load_2d(st + g * 2 * TC_BM * 128, &maps.r_hi, rb, nt * BN + g * 64, m0);
-                            if (x3) tma_load_2d(st + g * 2 * TC_BM * 128 + TC_BM * 128, &maps.r_lo, rb, nt * BN + g * 64, m0);
+                        for (int r = 0; r < RES_BLOCKS; ++r) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* st = smem + stage * S::STAGE_BYTES;
+                            uint64_t* rb = &res_full[(t_local & 1) * RES_BLOCKS + r];
+                            mbar_expect_tx(rb, (x3 ? 2u : 1u) * RES_G * TC_BM * 128);
+#pragma unroll
+                            for (int gg = 0; gg < RES_G; ++gg) {
+                                const int g = r * RES_G + gg;
+                                tma_load_2d(st + gg * 2 * TC_BM * 128, &maps.r_hi, rb, nt * BN + g * 64, m0);
+                                if (x3) tma_load_2d(st + gg * 2 * TC_BM * 128 + TC_BM * 128, &maps.r_lo, rb, nt * BN + g * 64, m0);
+                            }
+                            if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                         }
-                        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                     }
                     ++t_local;
                 }
@@ -191,13 +227,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
     } else if (warp == 1) {
         // ====================================== MMA issuer ======================================
+        // (PAIR_: the leader CTA issues for both; the peer's warp 1 only owns its TMEM allocation)
         // The whole warp walks the loop with warp-uniform values and elect.sync picks the issuing lane: descriptors
         // and barrier addresses then live in uniform registers and every UTCHMMA / UTCBAR issues straight, without
         // the ELECT / BRA.U.ANY waterfall ptxas wraps around per-thread operands.
-        {
+        if (!PAIR_ || cta_rank == 0) {
             // instruction descriptor: D = F32, A = B = F16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // pair form: M = 256 over the two CTAs, N = BN; each CTA supplies BN / 2 rows of the B operand
+            const uint32_t idesc_pair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+            (void)idesc_pair;
             const bool no_mma = (P.dbg & 2) != 0;                // measurement: loads + epilogue only
             const bool skip_res_slot = STAGED_ && P.res_hi != nullptr;
             const uint32_t smem_base = smem_u32(smem);
@@ -213,12 +253,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint64_t desc0 = make_sw128_desc(smem_base);   // A_hi of slot 0; everything else is + constant
             constexpr uint32_t SLOT16 = S::STAGE_BYTES >> 4, ALO16 = S::A_BYTES >> 4, B16 = (2 * S::A_BYTES) >> 4;
             bool ready = false;                                  // the probe already saw the next block
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
                 const uint32_t d1 = d0 + BN;
-                const bool last_tile = tile + (int)gridDim.x >= num_tiles;
+                const bool last_tile = tile + tile_step >= num_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (!ready) mbar_wait(&full_bar[stage], (full_bits >> stage) & 1u);
                     full_bits ^= 1u << stage;
@@ -231,7 +271,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         for (int k = 0; k < TC_BK / 16 - 1; ++k) {
                             const uint64_t adv = (uint64_t)(2 * k);                  // +32 bytes inside the swizzle row
                             const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-                            if (x3) {
+                            if constexpr (PAIR_) {
+                                // three N = BN pair instructions in the accumulation order of the single-CTA form
+                                const uint64_t b_lo = b_hi + (uint64_t)(S::B_BYTES >> 4);
+                                umma_f16_pair(d0, a_hi + adv, b_hi + adv, idesc_pair, accum);
+                                if (x3) {
+                                    umma_f16_pair(d1, a_hi + adv, b_lo + adv, idesc_pair, accum);
+                                    umma_f16_pair(d1, a_lo + adv, b_hi + adv, idesc_pair, 1u);
+                                }
+                            } else if (x3) {
                                 // [D0 | D1] += A_hi * [W_hi ; W_lo]^T as ONE N = 2*BN instruction (the two weight
                                 // tiles are contiguous in the stage, the two accumulators contiguous in TMEM):
                                 // A_hi is read from shared memory once instead of twice
@@ -246,20 +294,30 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     // where the next operand block sits: the slot after this one, one further at the end of a tile
                     // that carries a residual block
                     int nstage = stage + 1 == S::STAGES ? 0 : stage + 1;
-                    if (last_kb && skip_res_slot) nstage = nstage + 1 == S::STAGES ? 0 : nstage + 1;
+                    if (last_kb && skip_res_slot) nstage = (nstage + RES_BLOCKS) % S::STAGES;
                     ready = !(last_kb && last_tile) && mbar_test(&full_bar[nstage], (full_bits >> nstage) & 1u);
                     if (elect_one()) {
                         if (!no_mma) {
                             const uint64_t adv = (uint64_t)(2 * (TC_BK / 16 - 1));
-                            if (x3) {
+                            if constexpr (PAIR_) {
+                                const uint64_t b_lo = b_hi + (uint64_t)(S::B_BYTES >> 4);
+                                if (x3) umma_f16_pair(d1, a_lo + adv, b_hi + adv, idesc_pair, 1u);
+                                umma_f16_pair(d0, a_hi + adv, b_hi + adv, idesc_pair, 1u);
+                                if (x3) umma_f16_pair(d1, a_hi + adv, b_lo + adv, idesc_pair, 1u);
+                            } else if (x3) {
                                 umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
                                 umma_f16(d0, a_hi + adv, b_hi + adv, idesc_2n, 1u);
                             } else {
                                 umma_f16(d0, a_hi + adv, b_hi + adv, idesc, 1u);
                             }
                         }
-                        umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
-                        if (last_kb) umma_commit(&tfull_bar[acc]);
+                        if constexpr (PAIR_) {                   // both CTAs' slots / both CTAs' epilogues
+                            umma_commit_pair(&empty_bar[stage]);
+                            if (last_kb) umma_commit_pair(&tfull_bar[acc]);
+                        } else {
+                            umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
+                            if (last_kb) umma_commit(&tfull_bar[acc]);
+                        }
                     }
                     __syncwarp();
                     stage = nstage;
@@ -301,8 +359,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             int stage = 0, t_local = 0;                         // ring position of the residual blocks
             __half2 sat = __float2half2_rn(0.f);            // running max of |hi| (fp16 range guard)
             const bool masking = P.valid_w > 0;                 // kernel-uniform: canvases larger than the feature map
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int nt = tile % P.tiles_n, mt = (tile / P.tiles_n) * (PAIR_ ? 2 : 1) + (int)cta_rank;
                 bool row_valid = true;
                 if (masking) {                                  // this thread's output pixel inside the feature map?
                     const int rem = (mt * TC_BM + row) % (P.out_hw * P.out_wp);
@@ -312,14 +370,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     // residual tile -> registers (every epilogue thread waits on every use of res_full, in order),
                     // then the slot goes straight back to the producer
                     stage = (stage + num_kb) % S::STAGES;
-                    mbar_wait(&res_full[t_local & 1], (uint32_t)(t_local >> 1) & 1u);
+#pragma unroll
+                    for (int r = 0; r < RES_BLOCKS; ++r) {
+                    mbar_wait(&res_full[(t_local & 1) * RES_BLOCKS + r], (uint32_t)(t_local >> 1) & 1u);
                     const uint32_t rs = smem_u32(smem + stage * S::STAGE_BYTES);
 #pragma unroll
-                    for (int g = 0; g < NP; ++g)
+                    for (int gg = 0; gg < RES_G; ++gg)
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
-                            const uint4 h4 = lds128(rs + g * 2 * TC_BM * 128 + soff[q]);
-                            const uint4 l4 = x3 ? lds128(rs + g * 2 * TC_BM * 128 + TC_BM * 128 + soff[q]) : make_uint4(0, 0, 0, 0);
+                            const int g = r * RES_G + gg;
+                            const uint4 h4 = lds128(rs + gg * 2 * TC_BM * 128 + soff[q]);
+                            const uint4 l4 = x3 ? lds128(rs + gg * 2 * TC_BM * 128 + TC_BM * 128 + soff[q]) : make_uint4(0, 0, 0, 0);
                             const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -336,6 +397,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     group_bar(3, 512);
                     if (leader) mbar_arrive(&empty_bar[stage]);
                     stage = (stage + 1) % S::STAGES;
+                    }
                     ++t_local;
                 }
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -343,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 if (P.dbg & 4) {                                // measurement: main loop only
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) { if constexpr (PAIR_) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0)); else mbar_arrive(&tempty_bar[acc]); }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     continue;
                 }
@@ -359,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     if (g == NP - 1) {                          // last TMEM read of the tile: hand the accumulator back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        if (lane == 0) { if constexpr (PAIR_) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0)); else mbar_arrive(&tempty_bar[acc]); }
                     }
                     uint32_t oh[8], ol[8];
 #pragma unroll
@@ -424,8 +486,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (sat_hit(sat)) atomicAdd(P.sat_count, 1ull);
         } else {
             __half2 sat = __float2half2_rn(0.f);            // running max of |hi| (fp16 range guard)
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % P.tiles_n, mt = tile / P.tiles_n;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int nt = tile % P.tiles_n, mt = (tile / P.tiles_n) * (PAIR_ ? 2 : 1) + (int)cta_rank;
                 const long long m = (long long)mt * TC_BM + row;
                 const bool row_ok = m < P.M;
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -489,7 +551,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) { if constexpr (PAIR_) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0)); else mbar_arrive(&tempty_bar[acc]); }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (sat_hit(sat)) atomicAdd(P.sat_count, 1ull);
@@ -497,9 +559,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR_) cluster_sync_all();     // no CTA leaves (or frees TMEM) while its peer can still signal or be signalled
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (PAIR_)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -604,29 +670,40 @@ int encode_out_map(CUtensorMap* map, const __half* base, long long M, int Cout) 
     return encode_map(map, base, 2, dims, strides, box);
 }
 
-template <int BN, int STAGES, bool STAGED>
+template <int BN, int STAGES, bool STAGED, bool PAIR = false>
 static int launch_tc_variant(ivosw_ctx* c, const TcMaps& maps, const TcParams& P, cudaStream_t s) {
-    using S = TcSmem<BN, STAGES, STAGED>;
+    using S = TcSmem<BN, STAGES, STAGED, PAIR>;
     static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
     // the opt-in above 48 KB of dynamic shared memory is a per-DEVICE function attribute: one Engine per device may
     // live in the same process (engine.get_engine), so remember it per device, not per process
     static bool attr[64] = {};
     const int dv = c->device & 63;
     if (!attr[dv]) {
-        IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IVOSW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STAGED, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         S::TOTAL));
         attr[dv] = true;
     }
-    const int tiles = P.tiles_m * P.tiles_n;
-    const int grid = tiles < c->sm_count ? tiles : c->sm_count;
+    // PAIR: clusters of two CTAs (an SM pair of one TPC), one cluster per work item of two M tiles
+    const int tiles = PAIR ? (P.tiles_m / 2) * P.tiles_n : P.tiles_m * P.tiles_n;
+    const int slots = PAIR ? c->sm_count / 2 : c->sm_count;
+    const int grid = (tiles < slots ? tiles : slots) * (PAIR ? 2 : 1);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads(STAGED)); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = s;
-    cudaLaunchAttribute lattr[1];
-    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    lattr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute lattr[2];
+    int na = 0;
     static const bool pdl = !(getenv("IVOSW_PDL") && atoi(getenv("IVOSW_PDL")) == 0);
-    cfg.attrs = lattr; cfg.numAttrs = pdl ? 1 : 0;
-    IVOSW_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, STAGED>, maps, P));
+    if (pdl) {
+        lattr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        lattr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (PAIR) {
+        lattr[na].id = cudaLaunchAttributeClusterDimension;
+        lattr[na].val.clusterDim.x = 2; lattr[na].val.clusterDim.y = 1; lattr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = lattr; cfg.numAttrs = na;
+    IVOSW_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, STAGED, PAIR>, maps, P));
     c->launches += 1;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
@@ -675,8 +752,17 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
         if ((rc = encode_act_map(&maps.a2_hi, in2->hi, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
         if ((rc = encode_act_map(&maps.a2_lo, in2->lo, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
     }
-    if ((rc = encode_w_map(&maps.w_hi, fuse ? fuse->w_hi : L.w_hi, K, L.cout, BN))) return rc;
-    if ((rc = encode_w_map(&maps.w_lo, fuse ? fuse->w_lo : L.w_lo, K, L.cout, BN))) return rc;
+    // CTA pairs (cta_group::2): the compute-bound layers (conv1 / conv2: no residual, at least four K blocks) on the
+    // 128-wide staged variant with an even number of M tiles; the HBM-bound expand layers measured slower as pairs
+    // (res3.1.conv3 150 vs 108 us: two CTAs in lock step on one residual + output stream).  A CTA then ingests 48 instead of 64 KB per K block — one SM takes in ~79 B/clk, and 64 KB per 768 tensor
+    // cycles is more than that (scripts/umma_rate2.cu mode 14) — and the ring gets a fourth slot.  IVOSW_PAIR=0: off.
+    static const bool pair_ok = !(getenv("IVOSW_PAIR") && atoi(getenv("IVOSW_PAIR")) == 0);
+    static const int pair_mode = getenv("IVOSW_PAIR") ? atoi(getenv("IVOSW_PAIR")) : 1;   // 2: also the expand layers (measurement)
+    const bool expand = residual != nullptr || fuse != nullptr || L.is_downsample;
+    const bool pair = pair_ok && BN == 128 && K / TC_BK >= (expand ? 2 : 4) && (m_tiles % 2) == 0 &&
+                      (long long)B * L.out_hw * L.out_hw == m_tiles * TC_BM && (!expand || pair_mode == 2);
+    if ((rc = encode_w_map(&maps.w_hi, fuse ? fuse->w_hi : L.w_hi, K, L.cout, pair ? BN / 2 : BN))) return rc;
+    if ((rc = encode_w_map(&maps.w_lo, fuse ? fuse->w_lo : L.w_lo, K, L.cout, pair ? BN / 2 : BN))) return rc;
     if (staged) {
         if ((rc = encode_out_map(&maps.o_hi, out.hi, P.M, L.cout))) return rc;
         if ((rc = encode_out_map(&maps.o_lo, out.lo, P.M, L.cout))) return rc;
@@ -708,8 +794,10 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
         // one K block per tile (res2: Cin = 64): output/residual traffic is everything, two staging buffers
         // matter more than a third ring slot
         if (P.num_kb == 1 && getenv("IVOSW_NO_STAGED2") == nullptr) return launch_tc_variant<128, 2, true>(c, maps, P, s);
+        if (pair) return launch_tc_variant<128, 4, true, true>(c, maps, P, s);
         return launch_tc_variant<128, 3, true>(c, maps, P, s);
     }
+    if (pair) return launch_tc_variant<128, 4, false, true>(c, maps, P, s);
     return BN == 128 ? launch_tc_variant<128, 3, false>(c, maps, P, s) : launch_tc_variant<64, 4, false>(c, maps, P, s);
 }
 

@@ -7,7 +7,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "ivos-w_b200"))
 from ivosw import arch, synth
 from ivosw.engine import Engine
-B = 128
+B = int(os.environ.get("TC_CEILING_B", "128"))
 LAYERS = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [15, 28, 47, 27, 6, 16, 29, 48, 12, 25, 44]
 FLAGS = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3, 4]
 eng = Engine(0, "tc_fp16x3")

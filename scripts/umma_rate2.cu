@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) rate_kernel_opt(int iters, long lo
 // Mode 14: the optimised ring of mode 11 fed by REAL loads: a producer thread streams LOAD_BYTES per K block from an
 // L2-resident global buffer into the slot (cp.async.bulk, 16 KB pieces, completion on full[slot]) after waiting for
 // empty[slot].  64 KB per block is what the conv kernel loads; 48 / 32 KB model designs that deliver fewer bytes per SM.
-template <int LOAD_BYTES>
+template <int LOAD_BYTES, bool SPIN, bool NOMMA>
 __global__ void __launch_bounds__(THREADS, 1) rate_kernel_fed(int iters, long long* cycles, const uint8_t* gsrc, int region) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
@@ -312,11 +312,11 @@ __global__ void __launch_bounds__(THREADS, 1) rate_kernel_fed(int iters, long lo
             for (int slot = 0; slot < SLOTS; ++slot) {
                 const int it = it0 + slot;
                 if (it < iters) {
-                    if (!ready) mb_wait(&B.full[0][slot], ph);
+                    if (!ready) { if (SPIN) { while (!mb_test(&B.full[0][slot], ph)) {} } else mb_wait(&B.full[0][slot], ph); }
                     fence_after();
                     const uint64_t a_hi = base + (uint64_t)((slot * STAGE) >> 4), a_lo = a_hi + (A_BYTES >> 4), b = a_hi + (2 * A_BYTES >> 4);
                     const uint32_t d0 = tmem + (uint32_t)((it & 1) * 256);
-                    if (elect_one()) {
+                    if (!NOMMA && elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
                             mma(d0, a_hi + 2 * k, b + 2 * k, idesc_256, (it > 1 || k > 0) ? 1u : 0u);
@@ -327,8 +327,10 @@ __global__ void __launch_bounds__(THREADS, 1) rate_kernel_fed(int iters, long lo
                     const int nslot = (slot + 1) % SLOTS;
                     ready = (it + 1 < iters) && mb_test(&B.full[0][nslot], nslot == 0 ? ph ^ 1 : ph);
                     if (elect_one()) {
-                        mma(d0 + 128, a_lo + 6, b + 6, idesc_128, 1u);
-                        mma(d0, a_hi + 6, b + 6, idesc_256, 1u);
+                        if (!NOMMA) {
+                            mma(d0 + 128, a_lo + 6, b + 6, idesc_128, 1u);
+                            mma(d0, a_hi + 6, b + 6, idesc_256, 1u);
+                        }
                         commit(&B.empty[0][slot]);
                         if (it == iters - 1) commit(&B.done[0]);
                     }
@@ -342,8 +344,9 @@ __global__ void __launch_bounds__(THREADS, 1) rate_kernel_fed(int iters, long lo
         const uint8_t* src = gsrc + (size_t)blockIdx.x * region;
         uint32_t off = 0;
         for (int it = 0; it < iters; ++it) {
-            mb_wait(&B.empty[0][slot], ph ^ 1);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&B.full[0][slot])), "r"(LOAD_BYTES) : "memory");
+            if (SPIN) { while (!mb_test(&B.empty[0][slot], ph ^ 1)) {} } else mb_wait(&B.empty[0][slot], ph ^ 1);
+            if (LOAD_BYTES == 0) mb_arrive(&B.full[0][slot]);
+            else asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&B.full[0][slot])), "r"(LOAD_BYTES) : "memory");
 #pragma unroll
             for (int c = 0; c < LOAD_BYTES / CP_CHUNK; ++c) {
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -427,10 +430,10 @@ static void run_opt(const char* what, int iters, int sms) {
     CK(cudaFree(cyc));
 }
 
-template <int LOAD_BYTES>
+template <int LOAD_BYTES, bool SPIN = false, bool NOMMA = false>
 static void run_fed(int iters, int sms, const uint8_t* gsrc, int region) {
     const int smem = SLOTS * STAGE + 2048;
-    CK(cudaFuncSetAttribute(rate_kernel_fed<LOAD_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(rate_kernel_fed<LOAD_BYTES, SPIN, NOMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     long long* cyc;
     CK(cudaMalloc(&cyc, sizeof(long long) * sms));
     cudaEvent_t e0, e1;
@@ -438,7 +441,7 @@ static void run_fed(int iters, int sms, const uint8_t* gsrc, int region) {
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         CK(cudaEventRecord(e0));
-        rate_kernel_fed<LOAD_BYTES><<<sms, THREADS, smem>>>(iters, cyc, gsrc, region);
+        rate_kernel_fed<LOAD_BYTES, SPIN, NOMMA><<<sms, THREADS, smem>>>(iters, cyc, gsrc, region);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         CK(cudaGetLastError());
@@ -448,8 +451,8 @@ static void run_fed(int iters, int sms, const uint8_t* gsrc, int region) {
     long long h0;
     CK(cudaMemcpy(&h0, cyc, sizeof h0, cudaMemcpyDeviceToHost));
     const double flops = 4.0 * (2.0 * 128 * 256 * 16 + 2.0 * 128 * 128 * 16) * iters * sms;
-    printf("mode 14 optimised ring fed by bulk loads, %2d KB per K block, %4d KB region per CTA %8.3f ms %6.0f TFLOP/s %7.1f cycles/K-block  load %.1f B/clk/SM\n",
-           LOAD_BYTES / 1024, region / 1024, best, flops / best * 1e-9, (double)h0 / iters, (double)LOAD_BYTES * iters / (double)h0);
+    printf("mode 14%s%s optimised ring fed by bulk loads, %2d KB per K block, %4d KB region per CTA %8.3f ms %6.0f TFLOP/s %7.1f cycles/K-block  load %.1f B/clk/SM\n",
+           SPIN ? " SPIN" : "", NOMMA ? " NO-MMA" : "", LOAD_BYTES / 1024, region / 1024, best, flops / best * 1e-9, (double)h0 / iters, (double)LOAD_BYTES * iters / (double)h0);
     CK(cudaFree(cyc));
 }
 
@@ -485,6 +488,12 @@ int main() {
         run_fed<32768>(iters, sms, big, region);
         run_fed<16384>(iters, sms, big, region);
         run_fed<65536>(iters, sms, big, 192 * 1024);
+        run_fed<65536, true>(iters, sms, big, region);
+        run_fed<49152, true>(iters, sms, big, region);
+        run_fed<0, false, true>(iters, sms, big, region);
+        run_fed<0, true, true>(iters, sms, big, region);
+        run_fed<65536, false, true>(iters, sms, big, region);
+        run_fed<65536, true, true>(iters, sms, big, region);
     }
     return 0;
 }
