@@ -115,7 +115,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int num_tiles = PAIR_ ? (P.tiles_m >> 1) * P.tiles_n : P.tiles_m * P.tiles_n;
     const int num_kb = P.num_kb;
     const bool x3 = P.terms == 3;
-    constexpr uint32_t TMEM_COLS = 4 * BN;           // 2 accumulator stages x (D0, D1)
+    // (D0, D1) of one tile are 2 * BN columns: two accumulator stages when they fit the 512 columns (the epilogue of tile i
+    // then overlaps the MMAs of tile i + 1), one for the 256-wide pair tiles
+    constexpr int ACC_STAGES = 4 * BN <= 512 ? 2 : 1;
+    constexpr uint32_t TMEM_COLS = ACC_STAGES * 2 * BN;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
@@ -322,7 +325,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     __syncwarp();
                     stage = nstage;
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -406,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if constexpr (PAIR_) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0)); else mbar_arrive(&tempty_bar[acc]); }
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
                     continue;
                 }
 #pragma unroll
@@ -480,7 +483,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         bulk_commit();
                     }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
             if (leader) bulk_wait0();
             if (sat_hit(sat)) atomicAdd(P.sat_count, 1ull);
@@ -552,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if constexpr (PAIR_) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0)); else mbar_arrive(&tempty_bar[acc]); }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
             if (sat_hit(sat)) atomicAdd(P.sat_count, 1ull);
         }
@@ -752,15 +755,18 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
         if ((rc = encode_act_map(&maps.a2_hi, in2->hi, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
         if ((rc = encode_act_map(&maps.a2_lo, in2->lo, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
     }
-    // CTA pairs (cta_group::2): the compute-bound layers (conv1 / conv2: no residual, at least four K blocks) on the
+    // CTA pairs (cta_group::2): the compute-bound layers (conv1 / conv2: no residual, at least eight K blocks — res3.0.conv1 with four is HBM-bound and lost 20 % as pairs) on the
     // 128-wide staged variant with an even number of M tiles; the HBM-bound expand layers measured slower as pairs
     // (res3.1.conv3 150 vs 108 us: two CTAs in lock step on one residual + output stream).  A CTA then ingests 48 instead of 64 KB per K block — one SM takes in ~79 B/clk, and 64 KB per 768 tensor
     // cycles is more than that (scripts/umma_rate2.cu mode 14) — and the ring gets a fourth slot.  IVOSW_PAIR=0: off.
     static const bool pair_ok = !(getenv("IVOSW_PAIR") && atoi(getenv("IVOSW_PAIR")) == 0);
     static const int pair_mode = getenv("IVOSW_PAIR") ? atoi(getenv("IVOSW_PAIR")) : 1;   // 2: also the expand layers (measurement)
     const bool expand = residual != nullptr || fuse != nullptr || L.is_downsample;
-    const bool pair = pair_ok && BN == 128 && K / TC_BK >= (expand ? 2 : 4) && (m_tiles % 2) == 0 &&
-                      (long long)B * L.out_hw * L.out_hw == m_tiles * TC_BM && (!expand || pair_mode == 2);
+    // (the fused conv3 + downsample GEMMs of res4.0 / res5.0, 12 and 24 K blocks, are compute-bound too: 132 -> 120 and
+    //  125 -> 110 us as pairs, same box)
+    const bool want = expand ? (pair_mode == 2 || (fuse != nullptr && K / TC_BK >= 12)) : K / TC_BK >= 8;
+    const bool pair = pair_ok && BN == 128 && K / TC_BK >= 2 && (m_tiles % 2) == 0 &&
+                      (long long)B * L.out_hw * L.out_hw == m_tiles * TC_BM && want;
     if ((rc = encode_w_map(&maps.w_hi, fuse ? fuse->w_hi : L.w_hi, K, L.cout, pair ? BN / 2 : BN))) return rc;
     if ((rc = encode_w_map(&maps.w_lo, fuse ? fuse->w_lo : L.w_lo, K, L.cout, pair ? BN / 2 : BN))) return rc;
     if (staged) {
