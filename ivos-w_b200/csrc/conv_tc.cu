@@ -23,7 +23,9 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (the whole warp walks the loop,
 // elect.sync issues), then the epilogue warps: 16 in the staged variants (output through a shared-memory
 // staging buffer and TMA stores; used wherever a layer has at least two waves of tiles), 8 in the direct
-// variant (per-thread 16-byte stores; the few-tile res5 layers).  Persistent CTAs walk the (m-tile,
+// variant (per-thread 16-byte stores; the few-tile res5 layers).  The compute-bound layers run as CTA PAIRS
+// (template flag PAIR_, cta_group::2: two CTAs of a cluster share one M = 256 MMA, each staging its own A rows and half
+// of every weight plane; see the comment at launch_conv_tc and DESIGN.md 4.3).  Persistent CTAs walk the (m-tile,
 // n-tile) list n-fastest; TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Measurements behind these choices: DESIGN.md 4.3, profiles/r1_tc_ceiling.md.
 #include "tc_common.cuh"

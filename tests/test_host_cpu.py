@@ -61,15 +61,19 @@ def test_sass_is_blackwell_native(built_lib):
             fn = line.split("Function :")[1].strip()
             per_fn[fn] = set()
         elif fn:
-            for op in ("UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "HMMA.", "HGMMA"):
+            for op in ("UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "HMMA.", "HGMMA", "UTCHMMA.2CTA",
+                       "UTCBAR.2CTA.MULTICAST"):
                 if op in line:
                     per_fn[fn].add(op)
     conv = [f for f in per_fn if "conv_tc_kernel" in f or "conv_stack_kernel" in f]
     assert len(conv) >= 6
     for f in conv:
         assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= per_fn[f], (f, per_fn[f])
-    staged = [f for f in conv if "Lb1E" in f or "conv_stack" in f]
+    # conv_tc_kernel<BN, STAGES, STAGED, PAIR>: ...ELb<staged>ELb<pair>EE...
+    staged = [f for f in conv if "Lb1ELb" in f or "conv_stack" in f]
     assert staged and all("UTMASTG" in per_fn[f] for f in staged)
+    pairs = [f for f in conv if "ELb1EEEv" in f]          # cta_group::2 variants: pair MMAs and multicast commits
+    assert len(pairs) >= 2 and all({"UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST"} <= per_fn[f] for f in pairs)
     stem = [f for f in per_fn if "stem_tc_kernel" in f]
     assert stem and {"UTCHMMA", "UBLKCP", "LDTM"} <= per_fn[stem[0]]
     assert not any({"HMMA.", "HGMMA"} & ops for ops in per_fn.values())
