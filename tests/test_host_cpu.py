@@ -63,7 +63,10 @@ def test_sass_is_blackwell_native(built_lib):
         elif fn:
             for op in ("UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "HMMA.", "HGMMA", "UTCHMMA.2CTA",
                        "UTCBAR.2CTA.MULTICAST"):
-                if op in line:
+                if op == "HMMA.":                       # legacy mma.sync only: not the tail of UTCHMMA.2CTA
+                    if re.search(r"(?<![A-Z])HMMA\.", line):
+                        per_fn[fn].add(op)
+                elif op in line:
                     per_fn[fn].add(op)
     conv = [f for f in per_fn if "conv_tc_kernel" in f or "conv_stack_kernel" in f]
     assert len(conv) >= 6
