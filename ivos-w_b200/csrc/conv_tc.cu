@@ -829,8 +829,11 @@ int launch_conv_tc_g(ivosw_ctx* c, const GConv& L, const SplitAct& in, const Spl
         if ((rc = encode_act_map_g(&maps.a2_hi, in2->hi, B, L.in2_hp, L.in2_wp, L.cin2, L.stride2, L.out_hp, L.out_wp))) return rc;
         if ((rc = encode_act_map_g(&maps.a2_lo, in2->lo, B, L.in2_hp, L.in2_wp, L.cin2, L.stride2, L.out_hp, L.out_wp))) return rc;
     }
-    if ((rc = encode_w_map(&maps.w_hi, L.w_hi, K, L.cout, BN))) return rc;
-    if ((rc = encode_w_map(&maps.w_lo, L.w_lo, K, L.cout, BN))) return rc;
+    // CTA pairs for the compute-bound layers, as in launch_conv_tc
+    static const bool pair_ok = !(getenv("IVOSW_PAIR") && atoi(getenv("IVOSW_PAIR")) == 0);
+    const bool pair = pair_ok && BN == 128 && residual == nullptr && L.cin2 == 0 && K / TC_BK >= 8 && (P.M % (2 * TC_BM)) == 0;
+    if ((rc = encode_w_map(&maps.w_hi, L.w_hi, K, L.cout, pair ? BN / 2 : BN))) return rc;
+    if ((rc = encode_w_map(&maps.w_lo, L.w_lo, K, L.cout, pair ? BN / 2 : BN))) return rc;
     if ((rc = encode_out_map_ld(&maps.o_hi, out.hi, P.M, L.cout, out_ld))) return rc;
     if ((rc = encode_out_map_ld(&maps.o_lo, out.lo, P.M, L.cout, out_ld))) return rc;
     if (residual) {
@@ -858,6 +861,7 @@ int launch_conv_tc_g(ivosw_ctx* c, const GConv& L, const SplitAct& in, const Spl
                 fill_tap(P.taps[kh * L.k + kw], kh * L.dil - pad, kw * L.dil - pad, L.stride, L.cin);
     }
     if (BN == 64) return launch_tc_variant<64, 4, true>(c, maps, P, s);
+    if (pair) return launch_tc_variant<128, 4, true, true>(c, maps, P, s);
     return launch_tc_variant<128, 3, true>(c, maps, P, s);
 }
 
