@@ -757,15 +757,16 @@ int launch_conv_tc(ivosw_ctx* c, const ConvLayer& L, const SplitAct& in, const S
         if ((rc = encode_act_map(&maps.a2_hi, in2->hi, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
         if ((rc = encode_act_map(&maps.a2_lo, in2->lo, B, fuse->in_hw2, fuse->cin2, fuse->stride2, L.out_hw))) return rc;
     }
-    // CTA pairs (cta_group::2): the compute-bound layers (conv1 / conv2: no residual, at least eight K blocks — res3.0.conv1 with four is HBM-bound and lost 20 % as pairs) on the
-    // 128-wide staged variant with an even number of M tiles; the HBM-bound expand layers measured slower as pairs
-    // (res3.1.conv3 150 vs 108 us: two CTAs in lock step on one residual + output stream).  A CTA then ingests 48 instead of 64 KB per K block — one SM takes in ~79 B/clk, and 64 KB per 768 tensor
-    // cycles is more than that (scripts/umma_rate2.cu mode 14) — and the ring gets a fourth slot.  IVOSW_PAIR=0: off.
-    static const bool pair_ok = !(getenv("IVOSW_PAIR") && atoi(getenv("IVOSW_PAIR")) == 0);
-    static const int pair_mode = getenv("IVOSW_PAIR") ? atoi(getenv("IVOSW_PAIR")) : 1;   // 2: also the expand layers (measurement)
+    // CTA pairs (cta_group::2, template flag PAIR_): the compute-bound layers, when the number of M tiles is even —
+    //   * conv1 / conv2 (no residual) with at least eight K blocks (res3.0.conv1 with four is HBM-bound: 150 vs 127 us),
+    //   * the fused conv3 + downsample GEMMs of res4.0 / res5.0 (12 and 24 K blocks: 132 -> 120 and 125 -> 110 us).
+    // A CTA then ingests 48 instead of 64 KB per K block — one SM takes in ~79 B/clk and 64 KB per 768 tensor cycles is
+    // more than that (scripts/umma_rate2.cu mode 14) — and the ring gets a fourth slot.  The HBM-bound expand layers stay
+    // single-CTA: as pairs two CTAs walk one residual + output stream in lock step (res3.1.conv3 150 vs 108 us,
+    // res4.x.conv3 90 vs 75 us).  IVOSW_PAIR=0: off; IVOSW_PAIR=2: the expand layers too (measurement).
+    static const int pair_mode = getenv("IVOSW_PAIR") ? atoi(getenv("IVOSW_PAIR")) : 1;
+    const bool pair_ok = pair_mode != 0;
     const bool expand = residual != nullptr || fuse != nullptr || L.is_downsample;
-    // (the fused conv3 + downsample GEMMs of res4.0 / res5.0, 12 and 24 K blocks, are compute-bound too: 132 -> 120 and
-    //  125 -> 110 us as pairs, same box)
     const bool want = expand ? (pair_mode == 2 || (fuse != nullptr && K / TC_BK >= 12)) : K / TC_BK >= 8;
     const bool pair = pair_ok && BN == 128 && K / TC_BK >= 2 && (m_tiles % 2) == 0 &&
                       (long long)B * L.out_hw * L.out_hw == m_tiles * TC_BM && want;
