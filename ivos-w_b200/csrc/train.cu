@@ -10,11 +10,15 @@
 //   :266-268  clamp_(-1, 1) in place    the clamped value is what keeps accumulating
 //   :269      SGD(lr, momentum, wd)     d = g + wd * p;  buf = momentum * buf + d;  p -= lr * buf
 //
-// First CUDA path for this row: everything is fp32 on the CUDA cores (the activations and weights of a training step
-// need fp32 anyway; a tensor-core version needs dgrad / wgrad operand layouts the inference kernels do not have).
-//   forward conv / dgrad   conv_simt.cu's implicit-GEMM kernel; a data gradient is itself a convolution of dy with the
-//                          transposed, tap-flipped weight (stride 2: of the zero-upsampled dy; 1x1 stride 2: at low
-//                          resolution, then scattered to the even pixels)
+// Arithmetic: activations, parameters, gradients and optimiser state are fp32 (NHWC); where the FLOPs are —
+//   forward conv / dgrad   the bottleneck convolutions run on conv_tc.cu's tcgen05 kernel in its fp32-grade split-fp16 mode
+//                          (split x and w into hi / lo fp16 planes, convolve with an identity BatchNorm, merge; data gradients
+//                          are pre-scaled by a power of two taken from their largest magnitude so that 1e-8-sized values stay
+//                          inside fp16's normal range).  A data gradient is itself a convolution of dy with the transposed,
+//                          tap-flipped weight (stride 2: of the zero-upsampled dy; 1x1 stride 2: at low resolution, then
+//                          scattered to the even pixels).  conv_simt.cu's fp32 CUDA-core kernel remains for shapes the GEMM
+//                          tiling does not cover (B * OH * OW not a multiple of 128) and as IVOSW_TRAIN_TC=0 for validation;
+//                          the 4-channel stem is the fp32 direct convolution of stem.cu.
 //   wgrad                  dW[co][tap][ci] = sum_m dy[m][co] x[m @ tap][ci]: 64 x 64 tiles, the M axis split over CTAs into
 //                          partial sums, reduced in a fixed order (deterministic, no atomics)
 //   BatchNorm              per-channel sums in double, fixed-order reduction; backward with the batch-statistics terms
@@ -27,6 +31,8 @@
 #include "ivosw_internal.h"
 
 namespace ivosw {
+
+constexpr int TC_BM_ROWS = 128;      // pixels per GEMM tile of conv_tc.cu
 
 // conv_simt.cu
 int launch_conv_simt_raw(ivosw_ctx* c, const float* in, const float* wgt, const float* scale, const float* shift,
@@ -61,6 +67,8 @@ struct TrainState {
     std::vector<TrainLayer> L;                      // [0] stem, [1..52] bottleneck convolutions
     size_t fc_off = 0;
     DeviceBuffer arena, scratch, wt_arena, stats, ws;
+    DeviceBuffer tc_in, tc_out, tc_w;               // split-fp16 operand planes of the tensor-core convolutions
+    float* tc_scale = nullptr;                      // [2]: power-of-two pre-scale of a data gradient and its inverse
     float* identity_scale = nullptr;                // 2048 ones / zeros for raw convolutions
     float* identity_shift = nullptr;
     unsigned char* pool_idx = nullptr;
@@ -438,6 +446,90 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ gnew
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ host
+// ---------------------------------------------------------------------------------------------- tensor-core convolutions
+// Forward convolutions and data gradients of the bottleneck layers run on conv_tc.cu's tcgen05 kernel (split-fp16 operands,
+// fp32 accumulation: the fp32-grade arithmetic of the inference path).  The training step keeps fp32 NHWC activations, so
+// a convolution is: split x and w into (hi, lo) fp16 planes, conv_tc with an identity BatchNorm, merge the planes back.
+// Data gradients are tiny (1e-3 .. 1e-8, far below fp16's normal range): they are multiplied by a power of two chosen from
+// their largest magnitude while splitting and divided by it while merging — exact, and entirely on the device.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n4, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        m = fmaxf(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))), m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));     // non-negative floats order like their bits
+}
+// scale[0] = 2^e with max * 2^e in [512, 1024), scale[1] = 2^-e (1, 1 for an all-zero tensor); resets the max
+__global__ void pick_scale_kernel(unsigned int* __restrict__ maxbits, float* __restrict__ scale) {
+    const float m = __uint_as_float(*maxbits);
+    int e = 0;
+    if (m > 0.f && isfinite(m)) { int ex; frexpf(m, &ex); e = 10 - ex; }      // m = f * 2^ex, f in [0.5, 1)
+    e = max(-60, min(60, e));
+    scale[0] = ldexpf(1.f, e); scale[1] = ldexpf(1.f, -e);
+    *maxbits = 0u;
+}
+__global__ void __launch_bounds__(256) split_scaled_kernel(const float* __restrict__ in, __half* __restrict__ hi,
+                                                           __half* __restrict__ lo, long long n2, const float* __restrict__ scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const float sc = scale ? scale[0] : 1.f;
+    float2 v = reinterpret_cast<const float2*>(in)[i];
+    v.x = fminf(fmaxf(v.x * sc, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y * sc, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(v.x, v.y);
+    const float2 hf = __half22float2(h);
+    reinterpret_cast<__half2*>(hi)[i] = h;
+    reinterpret_cast<__half2*>(lo)[i] = __floats2half2_rn((v.x - hf.x) * 2048.0f, (v.y - hf.y) * 2048.0f);
+}
+__global__ void __launch_bounds__(256) merge_scaled_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                           float* __restrict__ out, long long n2, const float* __restrict__ scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const float inv = scale ? scale[1] : 1.f;
+    const float2 h = __half22float2(reinterpret_cast<const __half2*>(hi)[i]);
+    const float2 l = __half22float2(reinterpret_cast<const __half2*>(lo)[i]);
+    reinterpret_cast<float2*>(out)[i] = make_float2(fmaf(l.x, 1.0f / 2048.0f, h.x) * inv, fmaf(l.y, 1.0f / 2048.0f, h.y) * inv);
+}
+
+static bool train_tc_enabled() {
+    static const bool on = !(getenv("IVOSW_TRAIN_TC") && atoi(getenv("IVOSW_TRAIN_TC")) == 0);
+    return on;
+}
+static bool tc_eligible(int B, int cin, int out_hw, int cout) {
+    return train_tc_enabled() && cin % 64 == 0 && cout % 64 == 0 && ((long long)B * out_hw * out_hw) % TC_BM_ROWS == 0;
+}
+// y[B][out_hw][out_hw][cout] = conv(x[B][in_hw][in_hw][cin], w[cout][k][k][cin]); dyn_scale: x is a data gradient
+static int conv_f32_tc(ivosw_ctx* c, TrainState* T, const float* x, const float* w, float* y, int B, int in_hw, int cin, int out_hw,
+                       int cout, int k, int stride, int pad, bool dyn_scale, cudaStream_t s) {
+    const long long n_in = (long long)B * in_hw * in_hw * cin, n_out = (long long)B * out_hw * out_hw * cout;
+    const long long n_w = (long long)cout * k * k * cin;
+    const SplitAct in = split_view(T->tc_in), out = split_view(T->tc_out), ws = split_view(T->tc_w);
+    const float* sc = nullptr;
+    if (dyn_scale) {
+        unsigned int* mb = reinterpret_cast<unsigned int*>(T->tc_scale + 2);
+        absmax_kernel<<<592, 256, 0, s>>>(x, n_in / 4, mb);
+        pick_scale_kernel<<<1, 1, 0, s>>>(mb, T->tc_scale);
+        c->launches += 2;
+        sc = T->tc_scale;
+    }
+    split_scaled_kernel<<<(unsigned)((n_in / 2 + 255) / 256), 256, 0, s>>>(x, in.hi, in.lo, n_in / 2, sc);
+    split_scaled_kernel<<<(unsigned)((n_w / 2 + 255) / 256), 256, 0, s>>>(w, ws.hi, ws.lo, n_w / 2, nullptr);
+    c->launches += 2;
+    IVOSW_CUDA(cudaGetLastError());
+    ConvLayer L{};
+    L.cin = cin; L.cout = cout; L.k = k; L.stride = stride; L.pad = pad; L.in_hw = in_hw; L.out_hw = out_hw;
+    L.relu = false; L.residual = 0; L.is_downsample = false; L.first_of_block = false;
+    L.scale = T->identity_scale; L.shift = T->identity_shift; L.w_hi = ws.hi; L.w_lo = ws.lo;
+    int rc;
+    if ((rc = launch_conv_tc(c, L, in, nullptr, out, B, 3, s))) return rc;
+    merge_scaled_kernel<<<(unsigned)((n_out / 2 + 255) / 256), 256, 0, s>>>(out.hi, out.lo, y, n_out / 2, sc);
+    c->launches += 1;
+    IVOSW_CUDA(cudaGetLastError());
+    return IVOSW_OK;
+}
+
 static int n4(long long n) { return (int)((n / 4 + 255) / 256); }
 
 static int bn_forward(ivosw_ctx* c, TrainState* T, TrainLayer& L, long long M, const float* residual, int relu, cudaStream_t s) {
@@ -505,7 +597,9 @@ static int conv_dgrad(ivosw_ctx* c, TrainState* T, const TrainLayer& L, int B, c
     const long long n_in = (long long)B * L.in_hw * L.in_hw * L.cin;
     if (L.stride == 1) {
         float* dst = accumulate ? tmp_low : dx;
-        if ((rc = launch_conv_simt_raw(c, dy, L.wT, T->identity_scale, T->identity_shift, nullptr, dst, B, L.out_hw, L.cout, L.in_hw,
+        if (tc_eligible(B, L.cout, L.in_hw, L.cin)) {
+            if ((rc = conv_f32_tc(c, T, dy, L.wT, dst, B, L.out_hw, L.cout, L.in_hw, L.cin, L.k, 1, L.k - 1 - L.pad, true, s))) return rc;
+        } else if ((rc = launch_conv_simt_raw(c, dy, L.wT, T->identity_scale, T->identity_shift, nullptr, dst, B, L.out_hw, L.cout, L.in_hw,
                                        L.cin, L.k, 1, L.k - 1 - L.pad, 0, s)))
             return rc;
         if (accumulate) { add_inplace_kernel<<<n4(n_in), 256, 0, s>>>(dx, tmp_low, n_in / 4); c->launches += 1; }
@@ -514,12 +608,16 @@ static int conv_dgrad(ivosw_ctx* c, TrainState* T, const TrainLayer& L, int B, c
         zero_upsample_kernel<<<(unsigned)((up4 + 255) / 256), 256, 0, s>>>(dy, tmp_up, L.out_hw, L.cout, up4);
         c->launches += 1;
         float* dst = accumulate ? tmp_low : dx;
-        if ((rc = launch_conv_simt_raw(c, tmp_up, L.wT, T->identity_scale, T->identity_shift, nullptr, dst, B, L.in_hw, L.cout,
+        if (tc_eligible(B, L.cout, L.in_hw, L.cin)) {
+            if ((rc = conv_f32_tc(c, T, tmp_up, L.wT, dst, B, L.in_hw, L.cout, L.in_hw, L.cin, 3, 1, 1, true, s))) return rc;
+        } else if ((rc = launch_conv_simt_raw(c, tmp_up, L.wT, T->identity_scale, T->identity_shift, nullptr, dst, B, L.in_hw, L.cout,
                                        L.in_hw, L.cin, 3, 1, 1, 0, s)))
             return rc;
         if (accumulate) { add_inplace_kernel<<<n4(n_in), 256, 0, s>>>(dx, tmp_low, n_in / 4); c->launches += 1; }
     } else {                        // 1x1 stride 2: at low resolution, then scattered to the even pixels
-        if ((rc = launch_conv_simt_raw(c, dy, L.wT, T->identity_scale, T->identity_shift, nullptr, tmp_low, B, L.out_hw, L.cout,
+        if (tc_eligible(B, L.cout, L.out_hw, L.cin)) {
+            if ((rc = conv_f32_tc(c, T, dy, L.wT, tmp_low, B, L.out_hw, L.cout, L.out_hw, L.cin, 1, 1, 0, true, s))) return rc;
+        } else if ((rc = launch_conv_simt_raw(c, dy, L.wT, T->identity_scale, T->identity_shift, nullptr, tmp_low, B, L.out_hw, L.cout,
                                        L.out_hw, L.cin, 1, 1, 0, 0, s)))
             return rc;
         if (!accumulate) IVOSW_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * n_in, s));
@@ -538,9 +636,10 @@ void train_release(ivosw_ctx* c) {
     if (!T) return;
     float* shifted[] = {T->blob, T->gnew, T->gacc, T->mom};
     for (float* p : shifted) if (p) cudaFree(p - 2);
-    float* ptrs[] = {T->identity_scale, T->identity_shift, T->stem_wkc};
+    float* ptrs[] = {T->identity_scale, T->identity_shift, T->stem_wkc, T->tc_scale};
     for (float* p : ptrs) if (p) cudaFree(p);
     release(T->arena); release(T->scratch); release(T->wt_arena); release(T->stats); release(T->ws);
+    release(T->tc_in); release(T->tc_out); release(T->tc_w);
     delete T;
     c->train_state = nullptr;
 }
@@ -623,6 +722,14 @@ static int train_workspace(ivosw_ctx* c, TrainState* T, int B) {
     const size_t big = (size_t)B * 128 * 128 * 64;
     if ((rc = ensure(T->scratch, 5 * big * sizeof(float)))) return rc;
     if ((rc = ensure(T->stats, sizeof(double) * 2 * 256 * 2048 + sizeof(float) * 2 * 2048))) return rc;
+    // split-fp16 planes of the tensor-core convolutions: the largest activation (B x 64 x 64 x 256) and the largest weight
+    if ((rc = ensure(T->tc_in, sizeof(float) * (size_t)B * 64 * 64 * 256))) return rc;
+    if ((rc = ensure(T->tc_out, sizeof(float) * (size_t)B * 64 * 64 * 256))) return rc;
+    if ((rc = ensure(T->tc_w, sizeof(float) * (size_t)512 * 3 * 3 * 512))) return rc;
+    if (!T->tc_scale) {
+        IVOSW_CUDA(cudaMalloc(&T->tc_scale, sizeof(float) * 4));
+        IVOSW_CUDA(cudaMemset(T->tc_scale, 0, sizeof(float) * 4));
+    }
     // wire the inputs: block structure as in capi.cu
     const float* x = T->pool;
     const float *t1 = nullptr, *t2 = nullptr;
@@ -671,7 +778,10 @@ int train_step(ivosw_ctx* c, const UnitAddr& ua, int B, int H, int W, const floa
     for (size_t i = 1; i < T->L.size(); ++i) {
         const ConvLayer& Lh = c->layers[i - 1];
         TrainLayer& L = T->L[i];
-        if ((rc = launch_conv_simt_raw(c, L.x, T->blob + L.w_off, T->identity_scale, T->identity_shift, nullptr, L.y, B, L.in_hw,
+        if (tc_eligible(B, L.cin, L.out_hw, L.cout)) {
+            if ((rc = conv_f32_tc(c, T, L.x, T->blob + L.w_off, L.y, B, L.in_hw, L.cin, L.out_hw, L.cout, L.k, L.stride, L.pad, false, s)))
+                return rc;
+        } else if ((rc = launch_conv_simt_raw(c, L.x, T->blob + L.w_off, T->identity_scale, T->identity_shift, nullptr, L.y, B, L.in_hw,
                                        L.cin, L.out_hw, L.cout, L.k, L.stride, L.pad, 0, s)))
             return rc;
         const long long M = (long long)B * L.out_hw * L.out_hw;
