@@ -85,7 +85,13 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
     const int lane_row = threadIdx.x >> 5;                       // 8 row lanes
     const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(M, r0 + rows_per_split);
     double s = 0.0, q = 0.0;
-    for (long long r = r0 + lane_row; r < r1; r += 8) {
+    long long r = r0 + lane_row;
+    for (; r + 24 < r1; r += 32) {                    // four rows in flight per thread; same summation order as the tail loop
+        const float v0 = y[r * C + c], v1 = y[(r + 8) * C + c], v2 = y[(r + 16) * C + c], v3 = y[(r + 24) * C + c];
+        s += v0; q += (double)v0 * v0; s += v1; q += (double)v1 * v1;
+        s += v2; q += (double)v2 * v2; s += v3; q += (double)v3 * v3;
+    }
+    for (; r < r1; r += 8) {
         const float v = y[r * C + c];
         s += v; q += (double)v * v;
     }
@@ -148,7 +154,21 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restri
     const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(M, r0 + rows_per_split);
     const float m = mean[c], is = invstd[c];
     double sb = 0.0, sg = 0.0;
-    for (long long r = r0 + lane_row; r < r1; r += 8) {
+    long long r = r0 + lane_row;
+    for (; r + 24 < r1; r += 32) {                    // four rows (twelve loads) in flight per thread, same summation order
+        float dz[4], yv[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long o = (r + 8 * u) * C + c;
+            dz[u] = dout[o]; yv[u] = y[o]; av[u] = act ? act[o] : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float d = (av[u] > 0.f) ? dz[u] : 0.f;
+            sb += d; sg += (double)d * (double)((yv[u] - m) * is);
+        }
+    }
+    for (; r < r1; r += 8) {
         float dz = dout[r * C + c];
         if (act && !(act[r * C + c] > 0.f)) dz = 0.f;
         sb += dz; sg += (double)dz * (double)((y[r * C + c] - m) * is);
@@ -377,9 +397,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dy
     const int kh = tap / g.k, kw = tap - kh * g.k;
     const int ty = tid >> 4, tx = tid & 15;             // 16 x 16 threads, each 4 co x 4 k
     float acc[4][4] = {};
-    for (long long mb = m0; mb < m1; mb += 16) {
+    // one 16-row slab ahead: the next slab's global loads are issued before this slab's 256 FMAs per thread (the arithmetic
+    // and its order are unchanged)
+    auto load_slab = [&](long long mb, float4& dv, float4& xv) {
         const long long m = mb + lr;
-        float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        dv = make_float4(0.f, 0.f, 0.f, 0.f); xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < m1) {
             dv = __ldg(reinterpret_cast<const float4*>(dy + m * g.Cout + co0 + lc));
             if (k_ok) {
@@ -392,10 +414,15 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dy
                     xv = __ldg(reinterpret_cast<const float4*>(x + ((b * g.H + ih) * g.W + iw) * g.Cin + ci));
             }
         }
+    };
+    float4 dv, xv;
+    if (m0 < m1) load_slab(m0, dv, xv);
+    for (long long mb = m0; mb < m1; mb += 16) {
         __syncthreads();
         *reinterpret_cast<float4*>(&Ds[lr][lc]) = dv;
         *reinterpret_cast<float4*>(&Xs[lr][lc]) = xv;
         __syncthreads();
+        if (mb + 16 < m1) load_slab(mb + 16, dv, xv);
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const float4 d4 = *reinterpret_cast<const float4*>(&Ds[r][ty * 4]);
