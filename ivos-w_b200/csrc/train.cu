@@ -106,12 +106,27 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 }
 
 // mean / invstd of the batch; running statistics (momentum 0.1, unbiased variance) written into the blob
-__global__ void bn_finalize_kernel(const double* __restrict__ part, int splits, int C, long long M, float* __restrict__ mean,
-                                   float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// (block = 32 channels x 8 split lanes: lane j adds splits j, j + 8, ...; the eight partial sums are combined in a fixed order)
+__device__ __forceinline__ void sum_splits_8(const double* __restrict__ part, int splits, int C, int c, double& a, double& b) {
+    __shared__ double sh[2][8][32];
+    const int lane_row = threadIdx.x >> 5, cl = threadIdx.x & 31;
     double s = 0.0, q = 0.0;
-    for (int i = 0; i < splits; ++i) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+    if (c < C)
+        for (int i = lane_row; i < splits; i += 8) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+    sh[0][lane_row][cl] = s; sh[1][lane_row][cl] = q;
+    __syncthreads();
+    a = 0.0; b = 0.0;
+    if (lane_row == 0)
+        for (int i = 0; i < 8; ++i) { a += sh[0][i][cl]; b += sh[1][i][cl]; }
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int splits, int C, long long M,
+                                                          float* __restrict__ mean, float* __restrict__ invstd,
+                                                          float* __restrict__ run_mean, float* __restrict__ run_var) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s, q;
+    sum_splits_8(part, splits, C, c, s, q);
+    if ((threadIdx.x >> 5) != 0 || c >= C) return;
     const double m = s / (double)M;
     double var = q / (double)M - m * m;
     if (var < 0.0) var = 0.0;
@@ -183,12 +198,13 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restri
     }
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int splits, int C, float* __restrict__ dbeta,
-                                       float* __restrict__ dgamma, float* __restrict__ sums /*[2][C]*/) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double sb = 0.0, sg = 0.0;
-    for (int i = 0; i < splits; ++i) { sb += part[((size_t)i * C + c) * 2]; sg += part[((size_t)i * C + c) * 2 + 1]; }
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ part, int splits, int C,
+                                                              float* __restrict__ dbeta, float* __restrict__ dgamma,
+                                                              float* __restrict__ sums /*[2][C]*/) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double sb, sg;
+    sum_splits_8(part, splits, C, c, sb, sg);
+    if ((threadIdx.x >> 5) != 0 || c >= C) return;
     dbeta[c] = (float)sb; dgamma[c] = (float)sg;
     sums[c] = (float)sb; sums[C + c] = (float)sg;
 }
@@ -199,15 +215,27 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ y, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ sums, float inv_m, float* __restrict__ dy,
-                                                           float* __restrict__ dz_out, long long total, int C) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = (int)(i % C);
-    float dz = dout[i];
-    if (act && !(act[i] > 0.f)) dz = 0.f;
-    if (dz_out) dz_out[i] = dz;
-    const float xh = (y[i] - mean[c]) * invstd[c];
-    dy[i] = gamma[c] * invstd[c] * (dz - sums[c] * inv_m - xh * sums[C + c] * inv_m);
+                                                           float* __restrict__ dz_out, long long total4, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // four consecutive channels of one pixel
+    if (i >= total4) return;
+    const int c = (int)((i * 4) % C);
+    const float4 d4 = reinterpret_cast<const float4*>(dout)[i], y4 = reinterpret_cast<const float4*>(y)[i];
+    float dz[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    if (act) {
+        const float4 a4 = reinterpret_cast<const float4*>(act)[i];
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (!(av[u] > 0.f)) dz[u] = 0.f;
+    }
+    if (dz_out) reinterpret_cast<float4*>(dz_out)[i] = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float xh = (yv[u] - mean[c + u]) * invstd[c + u];
+        o[u] = gamma[c + u] * invstd[c + u] * (dz[u] - sums[c + u] * inv_m - xh * sums[C + c + u] * inv_m);
+    }
+    reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ---------------------------------------------------------------------------------------------- pooling / head
@@ -565,7 +593,7 @@ static int bn_forward(ivosw_ctx* c, TrainState* T, TrainLayer& L, long long M, c
     const int rows = (int)((M + splits - 1) / splits);
     double* part = (double*)T->stats.p;
     bn_stats_kernel<<<dim3(C / 32, splits), 256, 0, s>>>(L.y, M, C, rows, part);
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, splits, C, M, L.mean, L.invstd, T->blob + L.rm_off, T->blob + L.rv_off);
+    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(part, splits, C, M, L.mean, L.invstd, T->blob + L.rm_off, T->blob + L.rv_off);
     const long long tot4 = M * C / 4;
     bn_apply_kernel<<<(unsigned)((tot4 + 255) / 256), 256, 0, s>>>(L.y, L.mean, L.invstd, T->blob + L.g_off, T->blob + L.b_off,
                                                                   residual, L.a, tot4, C, relu);
@@ -584,10 +612,10 @@ static int bn_backward(ivosw_ctx* c, TrainState* T, TrainLayer& L, long long M, 
     float* sums = (float*)((char*)T->stats.p + sizeof(double) * 2 * 256 * 2048);
     const float* act = relu_masked ? L.a : nullptr;
     bn_bwd_stats_kernel<<<dim3(C / 32, splits), 256, 0, s>>>(dout, act, L.y, L.mean, L.invstd, M, C, rows, part);
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, splits, C, T->gnew + L.b_off, T->gnew + L.g_off, sums);
-    const long long tot = M * C;
-    bn_bwd_apply_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(dout, act, L.y, L.mean, L.invstd, T->blob + L.g_off, sums,
-                                                                     1.0f / (float)M, dy, dz_out, tot, C);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(part, splits, C, T->gnew + L.b_off, T->gnew + L.g_off, sums);
+    const long long tot4 = M * C / 4;
+    bn_bwd_apply_kernel<<<(unsigned)((tot4 + 255) / 256), 256, 0, s>>>(dout, act, L.y, L.mean, L.invstd, T->blob + L.g_off, sums,
+                                                                      1.0f / (float)M, dy, dz_out, tot4, C);
     c->launches += 3;
     IVOSW_CUDA(cudaGetLastError());
     return IVOSW_OK;
