@@ -548,9 +548,9 @@ __global__ void __launch_bounds__(256) merge_scaled_kernel(const __half* __restr
     reinterpret_cast<float2*>(out)[i] = make_float2(fmaf(l.x, 1.0f / 2048.0f, h.x) * inv, fmaf(l.y, 1.0f / 2048.0f, h.y) * inv);
 }
 
-static bool train_tc_enabled() {
-    static const bool on = !(getenv("IVOSW_TRAIN_TC") && atoi(getenv("IVOSW_TRAIN_TC")) == 0);
-    return on;
+static bool train_tc_enabled() {                 // read per call: tests compare the two arithmetic paths in one process
+    const char* e = getenv("IVOSW_TRAIN_TC");
+    return !(e && atoi(e) == 0);
 }
 static bool tc_eligible(int B, int cin, int out_hw, int cout) {
     return train_tc_enabled() && cin % 64 == 0 && cout % 64 == 0 && ((long long)B * out_hw * out_hw) % TC_BM_ROWS == 0;

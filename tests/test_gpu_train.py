@@ -101,3 +101,32 @@ def test_train_step_split_then_apply_equals_fused(golden_dir):
     for k in ("fc1.weight", "Encoder.conv1.weight", "Encoder.res4.3.conv3.weight", "Encoder.res2.0.bn1.bias"):
         np.testing.assert_array_equal(sa[k].numpy(), sb[k].numpy())
     a.close(); b.close()
+
+
+def test_train_step_tensor_core_path_matches_cuda_core_path(golden_dir, monkeypatch):
+    """Forward convolutions and data gradients run on the tcgen05 kernel (split-fp16, fp32-grade), or — IVOSW_TRAIN_TC=0 — on
+    the fp32 CUDA-core kernel.  Same batch, both paths: predictions / loss within the fp32 band, gradients within the 3 % of a
+    tensor's scale that any two fp32-grade paths differ by at batch 4 (module docstring).  With 3 samples the 8x8 layers (3 * 64 pixels: not a multiple of the 128-pixel GEMM tile) take the
+    CUDA-core kernel inside the tensor-core run, so the mixed dispatch is exercised too."""
+    from ivosw.engine import Engine
+    mg = _mg(golden_dir)
+    imgs, probs, targets, valid = mg.synth_train_batch(0)
+    outs = {}
+    for n in (4, 3):
+        F, P = torch.from_numpy(imgs[:n]).cuda(), torch.from_numpy(probs[:n]).cuda()
+        for tc in ("1", "0"):
+            monkeypatch.setenv("IVOSW_TRAIN_TC", tc)
+            e = Engine(0)
+            e.train_begin(mg.train_state_dict())
+            loss, pred = e.train_step(F, P, targets[:n], np.ones(n, bool), **mg.TRAIN_HP)
+            _, grads = e.train_export(want_grads=True)
+            outs[(n, tc)] = (loss, pred, {k: grads[k].numpy() for k in ("Encoder.conv1.weight", "Encoder.res2.0.conv1.weight",
+                                                                         "Encoder.res3.1.conv2.weight", "Encoder.res5.2.conv3.weight",
+                                                                         "Encoder.res4.0.downsample.0.weight", "fc1.weight")})
+            e.close()
+        (la, pa, ga), (lb, pb, gb) = outs[(n, "1")], outs[(n, "0")]
+        assert abs(la - lb) <= 1e-4 * abs(lb), (n, la, lb)
+        np.testing.assert_allclose(pa, pb, rtol=1e-4, atol=1e-4)
+        for k in ga:
+            scale = float(np.abs(gb[k]).max()) + 1e-12
+            assert float(np.abs(ga[k] - gb[k]).max()) <= 3e-2 * scale, (n, k, float(np.abs(ga[k] - gb[k]).max()), scale)
