@@ -474,6 +474,79 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dy
     }
 }
 
+// The same weight gradient on 128 x 128 tiles (layers with at least 128 output channels and 128 k values): every thread owns
+// 8 output channels x 8 k values, so a shared-memory row feeds 64 FMAs per four 16-byte reads (16 per two in the 64 x 64
+// kernel).  Row order and per-output summation order are those of wgrad_kernel.
+__global__ void __launch_bounds__(256) wgrad128_kernel(const float* __restrict__ dy, const float* __restrict__ x, WgradGeom g,
+                                                       float* __restrict__ part) {
+    __shared__ __align__(16) float Ds[16][128 + 4];
+    __shared__ __align__(16) float Xs[16][128 + 4];
+    const int tid = threadIdx.x;
+    const int k0 = blockIdx.x * 128, co0 = blockIdx.y * 128;
+    const long long m0 = (long long)blockIdx.z * g.rows_per_split, m1 = min(g.M, m0 + g.rows_per_split);
+    // loader: thread -> row (tid / 16) of the 16-row slab, two float4 at columns (tid % 16) * 4 and 64 + (tid % 16) * 4
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    int tapv[2], civ[2], khv[2], kwv[2]; bool okv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int kk = k0 + h * 64 + lc;
+        okv[h] = kk < g.K;
+        tapv[h] = okv[h] ? kk / g.Cin : 0; civ[h] = okv[h] ? kk - tapv[h] * g.Cin : 0;
+        khv[h] = tapv[h] / g.k; kwv[h] = tapv[h] - khv[h] * g.k;
+    }
+    const int ty = tid >> 4, tx = tid & 15;             // 16 x 16 threads: co = {ty*4.., 64+ty*4..}, k = {tx*4.., 64+tx*4..}
+    float acc[8][8] = {};
+    auto load_slab = [&](long long mb, float4* dv, float4* xv) {
+        const long long m = mb + lr;
+        dv[0] = dv[1] = xv[0] = xv[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < m1) {
+            dv[0] = __ldg(reinterpret_cast<const float4*>(dy + m * g.Cout + co0 + lc));
+            dv[1] = __ldg(reinterpret_cast<const float4*>(dy + m * g.Cout + co0 + 64 + lc));
+            const int ow = (int)(m % g.OW);
+            const long long t = m / g.OW;
+            const int oh = (int)(t % g.OH);
+            const long long b = t / g.OH;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!okv[h]) continue;
+                const int ih = oh * g.stride - g.pad + khv[h], iw = ow * g.stride - g.pad + kwv[h];
+                if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                    xv[h] = __ldg(reinterpret_cast<const float4*>(x + ((b * g.H + ih) * g.W + iw) * g.Cin + civ[h]));
+            }
+        }
+    };
+    float4 dv[2], xv[2];
+    if (m0 < m1) load_slab(m0, dv, xv);
+    for (long long mb = m0; mb < m1; mb += 16) {
+        __syncthreads();
+        *reinterpret_cast<float4*>(&Ds[lr][lc]) = dv[0]; *reinterpret_cast<float4*>(&Ds[lr][64 + lc]) = dv[1];
+        *reinterpret_cast<float4*>(&Xs[lr][lc]) = xv[0]; *reinterpret_cast<float4*>(&Xs[lr][64 + lc]) = xv[1];
+        __syncthreads();
+        if (mb + 16 < m1) load_slab(mb + 16, dv, xv);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float4 da = *reinterpret_cast<const float4*>(&Ds[r][ty * 4]), db = *reinterpret_cast<const float4*>(&Ds[r][64 + ty * 4]);
+            const float4 xa = *reinterpret_cast<const float4*>(&Xs[r][tx * 4]), xb = *reinterpret_cast<const float4*>(&Xs[r][64 + tx * 4]);
+            const float d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+            const float xx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(d[i], xx[j], acc[i][j]);
+        }
+    }
+    float* out = part + (size_t)blockIdx.z * g.Cout * g.K;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+            if (k < g.K) out[(size_t)co * g.K + k] = acc[i][j];
+        }
+    }
+}
+
 // grad[i] = sum over splits (fixed order)
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ grad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -626,7 +699,9 @@ static int conv_wgrad(ivosw_ctx* c, TrainState* T, const TrainLayer& L, int B, c
     g.B = B; g.H = L.in_hw; g.W = L.in_hw; g.Cin = L.cin; g.OH = L.out_hw; g.OW = L.out_hw; g.Cout = L.cout;
     g.k = L.k; g.stride = L.stride; g.pad = L.pad; g.K = L.k * L.k * L.cin;
     g.M = (long long)B * L.out_hw * L.out_hw;
-    const int tiles = ((g.K + 63) / 64) * (L.cout / 64);
+    const bool wide = L.cout % 128 == 0 && g.K >= 128 && !(getenv("IVOSW_WGRAD_WIDE") && atoi(getenv("IVOSW_WGRAD_WIDE")) == 0);
+    const int tile = wide ? 128 : 64;
+    const int tiles = ((g.K + tile - 1) / tile) * (L.cout / tile);
     long long splits = std::max<long long>(1, std::min<long long>(1184 / tiles + 1, g.M / 256));
     if (splits > 512) splits = 512;
     g.rows_per_split = (int)(((g.M + splits - 1) / splits + 15) / 16 * 16);
@@ -634,7 +709,8 @@ static int conv_wgrad(ivosw_ctx* c, TrainState* T, const TrainLayer& L, int B, c
     const size_t need = sizeof(float) * (size_t)splits * L.cout * g.K;
     int rc;
     if ((rc = ensure(T->ws, need))) return rc;
-    wgrad_kernel<<<dim3((g.K + 63) / 64, L.cout / 64, (unsigned)splits), 256, 0, s>>>(dy, x, g, (float*)T->ws.p);
+    if (wide) wgrad128_kernel<<<dim3((g.K + 127) / 128, L.cout / 128, (unsigned)splits), 256, 0, s>>>(dy, x, g, (float*)T->ws.p);
+    else wgrad_kernel<<<dim3((g.K + 63) / 64, L.cout / 64, (unsigned)splits), 256, 0, s>>>(dy, x, g, (float*)T->ws.p);
     const long long n = (long long)L.cout * g.K;
     reduce_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)T->ws.p, (int)splits, n, T->gnew + L.w_off);
     c->launches += 2;
